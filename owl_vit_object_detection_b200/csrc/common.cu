@@ -1,0 +1,82 @@
+#include "common.h"
+
+#include <mutex>
+#include <string.h>
+
+namespace owl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return static_cast<int>(e);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // libcuda is reached through the runtime, so the library links without -lcuda and loads on a
+    // machine without a driver (the CPU-only build box).
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches,
+                        uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return OWL_ERR_DRIVER;
+  }
+  OWL_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p not 16-byte aligned", base);
+  OWL_CHECK_ARG((row_stride * 2) % 16 == 0, "tensor map: row stride %llu elements is not a multiple of 16 bytes",
+                (unsigned long long)row_stride);
+  OWL_CHECK_ARG(batches <= 1 || (batch_stride * 2) % 16 == 0, "tensor map: batch stride not a multiple of 16 bytes");
+  OWL_CHECK_ARG(inner > 0 && rows > 0 && batches > 0, "tensor map: empty dimension");
+  cuuint64_t dims[3] = {inner, rows, batches};
+  cuuint64_t strides[2] = {row_stride * 2, (batches > 1 ? batch_stride : rows * row_stride) * 2};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner %llu rows %llu batches %llu ld %llu)",
+              static_cast<int>(r), (unsigned long long)inner, (unsigned long long)rows,
+              (unsigned long long)batches, (unsigned long long)row_stride);
+    return OWL_ERR_DRIVER;
+  }
+  return OWL_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace owl
+
+extern "C" const char* owl_last_error(void) { return owl::g_err; }
+extern "C" int owl_abi_version(void) { return 1; }

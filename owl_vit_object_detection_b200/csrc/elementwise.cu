@@ -1,0 +1,396 @@
+// HBM-bound forward kernels around the GEMMs: patch gather + cast, LayerNorm, the fused
+// post-LN x CLS x LN tail, class-head normalisation, box-head tail, softmax rows, casts.
+// One warp per row, 128-bit loads, fp32 statistics; all grids are sized from the row count.
+#include "common.h"
+#include <cuda_fp16.h>
+
+namespace owl {
+
+constexpr int ROW_WARPS = 8;       // warps (rows) per CTA
+constexpr int MAX_VEC = 8;         // row length <= 8 * 128 floats
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ------------------------------------------------------------------ patch gather (HF:336 conv k = s = patch)
+// img [B,3,IS,IS] fp32 NCHW -> patches [B*g*g, ld] fp16, column = c*ps*ps + ky*ps + kx (conv-weight order).
+template <int VEC>
+__global__ void im2col_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int IS, int ps,
+                              int ld) {
+  const int g = IS / ps;
+  const long long groups_per_row = IS / VEC;
+  const long long total = 1LL * B * 3 * IS * groups_per_row;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int xg = static_cast<int>(i % groups_per_row);
+    long long r = i / groups_per_row;
+    const int y = static_cast<int>(r % IS);
+    r /= IS;
+    const int c = static_cast<int>(r % 3);
+    const int b = static_cast<int>(r / 3);
+    const int x = xg * VEC;
+    const float* src = img + ((1LL * b * 3 + c) * IS + y) * IS + x;
+    const int py = y / ps, ky = y - py * ps, px = x / ps, kx = x - px * ps;
+    __half* dst = out + (1LL * b * g * g + py * g + px) * ld + (c * ps + ky) * ps + kx;
+    if constexpr (VEC == 8) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
+      __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(dst) = u;
+    } else {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+      *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(v.x, v.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (HF:498,507,768; eps 1e-5)
+// y[r] = LN(x[r]) * gamma + beta.  Row r is read at x + r * x_stride (so a strided subset of rows, e.g.
+// the CLS rows, can be normalised).  If `cls_emb` is set, rows with r % tokens == 0 take their input
+// from cls_emb + pos[0] instead (the CLS row of the embedding, HF:338-343).
+template <typename OutT>
+__global__ void layernorm_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, OutT* __restrict__ y, long long y_stride,
+                                 int rows, int D, float eps, const float* __restrict__ cls_emb,
+                                 const float* __restrict__ pos0, int tokens) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  float4 v[MAX_VEC];
+  const bool is_cls = cls_emb != nullptr && (row % tokens) == 0;
+  const float* xr = x + row * x_stride;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      if (is_cls) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(cls_emb + c));
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pos0 + c));
+        v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+      } else {
+        v[i] = *reinterpret_cast<const float4*>(xr + c);
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  OutT* yr = y + row * y_stride;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      store4(yr + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ reference src/models.py:80-86 fused
+// feats[b,p] = LN2( LN1(x[b,1+p]) * ecls[b] )  with ecls[b] = LN1(x[b,0]) precomputed (fp32 [B,D]).
+__global__ void post_fuse_kernel(const float* __restrict__ x, const float* __restrict__ ecls,
+                                 const float* __restrict__ g1, const float* __restrict__ b1,
+                                 const float* __restrict__ g2, const float* __restrict__ b2,
+                                 __half* __restrict__ feats, int B, int P, int D, float eps) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= B * P) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  const int b = row / P, p = row - b * P;
+  const float* xr = x + (1LL * b * (P + 1) + 1 + p) * D;
+  const float* cr = ecls + 1LL * b * D;
+  float4 v[MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nv) {
+      v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+  float rstd = rsqrtf(warp_sum(q) / D + eps);
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(g1 + c));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(b1 + c));
+      const float4 cl = __ldg(reinterpret_cast<const float4*>(cr + c));
+      v[i].x = ((v[i].x - mean) * rstd * g.x + be.x) * cl.x;
+      v[i].y = ((v[i].y - mean) * rstd * g.y + be.y) * cl.y;
+      v[i].z = ((v[i].z - mean) * rstd * g.z + be.z) * cl.z;
+      v[i].w = ((v[i].w - mean) * rstd * g.w + be.w) * cl.w;
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  mean = warp_sum(s) / D;
+  q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+  rstd = rsqrtf(warp_sum(q) / D + eps);
+  __half* fr = feats + 1LL * row * D;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nv) {
+      const int c = i * 128 + lane * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(g2 + c));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(b2 + c));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + be.x;
+      o.y = (v[i].y - mean) * rstd * g.y + be.y;
+      o.z = (v[i].z - mean) * rstd * g.z + be.z;
+      o.w = (v[i].w - mean) * rstd * g.w + be.w;
+      store4(fr + c, o);
+    }
+}
+
+// ------------------------------------------------------------------ class head normalisations
+// reference src/models.py:28-30  e / (||e|| + 1e-6)      (mode 0, image side)
+// reference src/models.py:31-33  q / ||q|| + 1e-6        (mode 1, query side; precedence quirk Q1)
+__global__ void rownorm_kernel(const float* __restrict__ e, __half* __restrict__ out, int rows, int E, int mode) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = E >> 7;
+  const float* er = e + 1LL * row * E;
+  float4 v[MAX_VEC];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nv) {
+      v[i] = *reinterpret_cast<const float4*>(er + i * 128 + lane * 4);
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  const float nrm = sqrtf(warp_sum(q));
+  __half* orow = out + 1LL * row * E;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nv) {
+      float4 o;
+      if (mode == 0) {
+        const float inv = 1.0f / (nrm + 1e-6f);
+        o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+      } else {
+        o = make_float4(v[i].x / nrm + 1e-6f, v[i].y / nrm + 1e-6f, v[i].z / nrm + 1e-6f, v[i].w / nrm + 1e-6f);
+      }
+      store4(orow + i * 128 + lane * 4, o);
+    }
+}
+
+// ------------------------------------------------------------------ box head tail
+// HF:1024 dense2 (D -> 4) + reference src/models.py:71-73: + box bias, sigmoid, cxcywh -> xyxy.
+// h [M,D] fp16, w [4,D] fp32, bias [4], box_bias [P,4]; boxes [M,4] fp32, sig [M,4] fp32 (saved for bwd).
+__global__ void box_tail_kernel(const __half* __restrict__ h, const float* __restrict__ w,
+                                const float* __restrict__ bias, const float* __restrict__ box_bias,
+                                float* __restrict__ boxes, float* __restrict__ sig, int M, int P, int D) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const __half* hr = h + 1LL * row * D;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(hr + c);
+    const __half2* hp = reinterpret_cast<const __half2*>(&u);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(hp[j]);
+      x[2 * j] = f.x; x[2 * j + 1] = f.y;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + 1LL * o * D + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + 1LL * o * D + c + 4));
+      acc[o] += x[0] * w0.x + x[1] * w0.y + x[2] * w0.z + x[3] * w0.w + x[4] * w1.x + x[5] * w1.y +
+                x[6] * w1.z + x[7] * w1.w;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
+  if (lane == 0) {
+    const int p = row % P;
+    float s[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float z = acc[o] + bias[o] + box_bias[p * 4 + o];
+      s[o] = 1.0f / (1.0f + expf(-z));
+    }
+    *reinterpret_cast<float4*>(sig + 4LL * row) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(boxes + 4LL * row) =
+        make_float4(s[0] - 0.5f * s[2], s[1] - 0.5f * s[3], s[0] + 0.5f * s[2], s[1] + 0.5f * s[3]);
+  }
+}
+
+// ------------------------------------------------------------------ softmax over rows of fp16 scores (in place)
+// HF:398 softmax in fp32; rows of length n inside a [rows, ld] buffer; columns >= n are left untouched.
+__global__ void softmax_rows_kernel(__half* __restrict__ s, long long rows, int n, int ld) {
+  const long long row = blockIdx.x * 1LL * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  __half* r = s + row * ld;
+  float v[32];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < n ? __half2float(r[c]) : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = (lane + 32 * i) < n ? __expf(v[i] - m) : 0.f;
+    sum += v[i];
+  }
+  const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < n) r[c] = __float2half_rn(v[i] * inv);
+  }
+}
+
+// ------------------------------------------------------------------ fp32 -> fp16 cast with scale
+__global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n, float scale) {
+  const long long i = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    store4(dst + i, make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale));
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2half_rn(src[j] * scale);
+  }
+}
+
+}  // namespace owl
+
+using namespace owl;
+
+static inline int row_blocks(long long rows) { return static_cast<int>((rows + ROW_WARPS - 1) / ROW_WARPS); }
+
+extern "C" int owl_im2col_f16(const float* img, void* out, int B, int image_size, int patch, long long ld,
+                              void* stream) {
+  OWL_CHECK_ARG(img && out && B > 0 && patch > 0 && image_size % patch == 0, "im2col: bad arguments");
+  OWL_CHECK_ARG(image_size % 8 == 0 && patch % 2 == 0, "im2col: image_size %% 8 and patch %% 2 must be 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool v8 = patch % 8 == 0 && ld % 8 == 0;
+  const long long total = 1LL * B * 3 * image_size * (image_size / (v8 ? 8 : 2));
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  if (v8) im2col_kernel<8><<<blocks, 256, 0, s>>>(img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
+  else im2col_kernel<2><<<blocks, 256, 0, s>>>(img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_layernorm(const float* x, long long x_stride, const float* gamma, const float* beta, void* y,
+                             long long y_stride, int out_f16, int rows, int D, float eps, const float* cls_emb,
+                             const float* pos0, int tokens, void* stream) {
+  OWL_CHECK_ARG(x && gamma && beta && y && rows > 0, "layernorm: null / empty argument");
+  OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * MAX_VEC, "layernorm: D = %d must be a multiple of 128 and <= %d", D,
+                128 * MAX_VEC);
+  OWL_CHECK_ARG(!cls_emb || (pos0 && tokens > 0), "layernorm: cls_emb needs pos0 and tokens");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_f16)
+    layernorm_kernel<__half><<<row_blocks(rows), ROW_WARPS * 32, 0, s>>>(x, x_stride, gamma, beta,
+        static_cast<__half*>(y), y_stride, rows, D, eps, cls_emb, pos0, tokens);
+  else
+    layernorm_kernel<float><<<row_blocks(rows), ROW_WARPS * 32, 0, s>>>(x, x_stride, gamma, beta,
+        static_cast<float*>(y), y_stride, rows, D, eps, cls_emb, pos0, tokens);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_post_fuse(const float* x, const float* ecls, const float* g1, const float* b1, const float* g2,
+                             const float* b2, void* feats, int B, int P, int D, float eps, void* stream) {
+  OWL_CHECK_ARG(x && ecls && g1 && b1 && g2 && b2 && feats && B > 0 && P > 0, "post_fuse: null / empty argument");
+  OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * MAX_VEC, "post_fuse: unsupported D = %d", D);
+  post_fuse_kernel<<<row_blocks(1LL * B * P), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ecls, g1, b1, g2, b2, static_cast<__half*>(feats), B, P, D, eps);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_rownorm_f16(const float* e, void* out, int rows, int E, int query_mode, void* stream) {
+  OWL_CHECK_ARG(e && out && rows > 0, "rownorm: null / empty argument");
+  OWL_CHECK_ARG(E % 128 == 0 && E <= 128 * MAX_VEC, "rownorm: unsupported E = %d", E);
+  rownorm_kernel<<<row_blocks(rows), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      e, static_cast<__half*>(out), rows, E, query_mode);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_box_tail(const void* h, const float* w, const float* bias, const float* box_bias, float* boxes,
+                            float* sig, int M, int P, int D, void* stream) {
+  OWL_CHECK_ARG(h && w && bias && box_bias && boxes && sig && M > 0 && P > 0, "box_tail: null / empty argument");
+  OWL_CHECK_ARG(D % 8 == 0, "box_tail: D %% 8 != 0");
+  box_tail_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(h), w, bias, box_bias, boxes, sig, M, P, D);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_softmax_rows_f16(void* scores, long long rows, int n, int ld, void* stream) {
+  OWL_CHECK_ARG(scores && rows > 0 && n > 0 && n <= 1024 && ld >= n, "softmax_rows: bad arguments (n <= 1024)");
+  softmax_rows_kernel<<<row_blocks(rows), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__half*>(scores), rows, n, ld);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_cast_f16(const float* src, void* dst, long long n, float scale, void* stream) {
+  OWL_CHECK_ARG(src && dst && n > 0, "cast_f16: null / empty argument");
+  OWL_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                "cast_f16: misaligned pointers");
+  const long long threads = (n + 3) / 4;
+  cast_f16_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__half*>(dst), n, scale);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}

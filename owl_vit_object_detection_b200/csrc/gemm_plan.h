@@ -1,0 +1,51 @@
+// Host-side GEMM plan: tensor maps + shape + epilogue parameters, built once and launched many times.
+#pragma once
+#include "common.h"
+#include "gemm_tc.cuh"
+
+namespace owl {
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmShape gs;
+  int bn;
+  int a_mn, b_mn;
+  int epilogue;  // 0 f16, 1 f32, 2 pool3
+  EpiF16::Params p16;
+  EpiF32::Params p32;
+  EpiPool3::Params pp;
+  int grid;
+};
+
+// `bn` = 0 lets the planner choose the N tile.
+int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan);
+int gemm_plan_launch(const GemmPlan& plan, cudaStream_t stream);
+
+// per-major-combination launchers (one translation unit each, so they compile in parallel)
+int gemm_launch_kk(const GemmPlan& p, cudaStream_t s);
+int gemm_launch_kmn(const GemmPlan& p, cudaStream_t s);
+int gemm_launch_mnmn(const GemmPlan& p, cudaStream_t s);
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int gemm_launch_one(const GemmPlan& p, const typename Epi::Params& ep, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN)));
+    configured = true;
+  }
+  kern<<<p.grid, GEMM_THREADS, gemm_smem_bytes(BN), s>>>(p.tmA, p.tmB, p.gs, ep);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+#define OWL_GEMM_DISPATCH_BN(A_MN, B_MN, EPI, params)                                         \
+  switch (p.bn) {                                                                             \
+    case 64:  return gemm_launch_one<64, A_MN, B_MN, EPI>(p, params, s);                      \
+    case 128: return gemm_launch_one<128, A_MN, B_MN, EPI>(p, params, s);                     \
+    case 192: return gemm_launch_one<192, A_MN, B_MN, EPI>(p, params, s);                     \
+    case 256: return gemm_launch_one<256, A_MN, B_MN, EPI>(p, params, s);                     \
+    default: set_error("gemm: unsupported N tile %d", p.bn); return OWL_ERR_UNSUPPORTED;      \
+  }
+
+}  // namespace owl
