@@ -74,6 +74,63 @@ typedef struct owl_gemm_args {
 
 int owl_gemm(const owl_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound forward kernels around the GEMMs (one warp per row, 128-bit accesses, fp32 statistics).
+ */
+/* HF:336 patch-embedding conv (kernel = stride = patch, no bias) as a gather: img [B,3,IS,IS] f32 NCHW ->
+ * patches [B*(IS/patch)^2, ld] fp16 with column = c*patch^2 + ky*patch + kx (the conv weight's own order). */
+int owl_im2col_f16(const float* img, void* patches, int B, int image_size, int patch, long long ld, void* stream);
+/* HF:498,507,768 + reference src/models.py:80,86 LayerNorm over rows of length D (fp32 in; fp16 or fp32 out).
+ * Row r is read at x + r*x_stride and written at y + r*y_stride.  When cls_emb != NULL, rows with
+ * r %% tokens == 0 are replaced by cls_emb + pos0 first (the CLS row of the embedding, HF:338-343). */
+int owl_layernorm(const float* x, long long x_stride, const float* gamma, const float* beta, void* y,
+                  long long y_stride, int out_f16, int rows, int D, float eps, const float* cls_emb,
+                  const float* pos0, int tokens, void* stream);
+/* reference src/models.py:80-86 fused: feats[b,p] = LN2(LN1(x[b,1+p]) * ecls[b]), ecls[b] = LN1(x[b,0]). */
+int owl_post_fuse(const float* x, const float* ecls, const float* g1, const float* b1, const float* g2,
+                  const float* b2, void* feats_f16, int B, int P, int D, float eps, void* stream);
+/* reference src/models.py:28-33: query_mode 0: e/(||e||+1e-6)   query_mode 1: q/||q|| + 1e-6.  fp16 out. */
+int owl_rownorm_f16(const float* e, void* out_f16, int rows, int E, int query_mode, void* stream);
+/* HF:1024 dense2 + reference src/models.py:71-73: boxes = corners(sigmoid(h W^T + b + box_bias)); also
+ * stores the sigmoid output (cx,cy,w,h) for the backward pass. */
+int owl_box_tail(const void* h_f16, const float* w, const float* bias, const float* box_bias, float* boxes,
+                 float* sig, int M, int P, int D, void* stream);
+/* HF:398 softmax over the first n columns of each row of an fp16 [rows, ld] buffer, in place (n <= 1024). */
+int owl_softmax_rows_f16(void* scores_f16, long long rows, int n, int ld, void* stream);
+int owl_cast_f16(const float* src, void* dst_f16, long long n, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matcher + loss (reference src/matcher.py:85-159, src/losses.py:16-116), device-resident.
+ * Targets are padded: labels [B,Tmax] i64, tboxes [B,Tmax,4] f32 xyxy, num_targets [B] i32.
+ * `status` is a device int, OR-ed with 1 for a degenerate box (the reference asserts, src/matcher.py:34-35)
+ * and 2 for an infeasible assignment; the caller zeroes it and checks it when it syncs anyway.
+ */
+/* src/matcher.py:103-131.  costT [B,Tmax,P] f32 (target-major so that the solver's scans are coalesced):
+ * costT[b][t][p] = (L1(box_p, tbox_t) - softmax(sims[b,p])[label_t]) - GIoU(box_p, tbox_t). */
+int owl_matcher_cost(const float* sims, const float* boxes, const long long* labels, const float* tboxes,
+                     const int* num_targets, float* costT, int B, int P, int C, int Tmax, int* status,
+                     void* stream);
+/* src/matcher.py:135-137 (scipy.optimize.linear_sum_assignment).  match_pred [B,Tmax] i32: prediction assigned
+ * to each target, -1 for padding.  Index-exact with SciPy including its tie rule whenever num_targets < P
+ * (SciPy transposes the problem only when rows > cols; the reference always has P = 576 > T). */
+int owl_lsap(const float* costT, const int* num_targets, int B, int P, int Tmax, int* match_pred, int* status,
+             void* stream);
+/* src/matcher.py:138-159 + src/losses.py:42-69,100-108,16-40.
+ *   tc_matched [B,P] i64  target_classes as the matcher returns them (background = bg_label)
+ *   tc_final   [B,P] i64  after the IoU>0.85 ordered label sweep (src/losses.py:100-106)
+ *   pred_sorted / tgt_sorted [B,Tmax] i64  the matcher's `indices` (sorted by prediction), -1 padded
+ *   losses_per_image [B,4], losses_mean4 [4]  (loss_ce, loss_bg, loss_bbox, loss_giou)
+ *   dsims_unit [B,P,C], dl1 / dgiou [B,Tmax,4]  gradients for unit upstream grads, incl. the 1/B of the mean */
+int owl_match_loss(const float* sims, const float* boxes, const long long* labels, const float* tboxes,
+                   const int* num_targets, const int* match_pred, const float* scales, int B, int P, int C,
+                   int Tmax, int bg_label, long long* tc_matched, long long* tc_final, long long* pred_sorted,
+                   long long* tgt_sorted, float* losses_per_image, float* losses_mean4, float* dsims_unit,
+                   float* dl1, float* dgiou, void* stream);
+/* autograd of the four losses: upstream4 = d(total)/d(loss_ce, loss_bg, loss_bbox, loss_giou) on the device. */
+int owl_loss_backward(const float* dsims_unit, const long long* tc_final, const int* match_pred, const float* dl1,
+                      const float* dgiou, const float* upstream4, int B, int P, int C, int Tmax, int bg_label,
+                      float* dsims, float* dboxes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 // post-LN x CLS x LN tail, class-head normalisation, box-head tail, softmax rows, casts.
 // One warp per row, 128-bit loads, fp32 statistics; all grids are sized from the row count.
 #include "common.h"
+#include <algorithm>
 #include <cuda_fp16.h>
 
 namespace owl {

@@ -1,0 +1,218 @@
+"""Forward / backward of the OWL-ViT hot path as a fixed sequence of libowl_b200.so kernel launches.
+
+Mirrors, step for step (HF = transformers/models/owlvit/modeling_owlvit.py as cited in SURVEY.md):
+  reference src/models.py:98-119  OwlViT.forward          -> Engine.forward
+  reference src/models.py:77-96   image_embedder + HF:757-782 vision tower
+  reference src/models.py:65-73   box_predictor  + HF:1009-1025
+  reference src/models.py:24-38   PatchedOwlViTClassPredictionHead.forward
+  reference main.py:90            loss.backward() under the reference freeze rule -> Engine.backward
+
+This module only sequences kernels and owns buffers (torch is used for device memory and streams);
+every arithmetic op runs in a hand-written sm_100a kernel.  There is no CPU / torch fallback.
+
+Data layout in HBM (B images, S = P + 1 tokens, D hidden):
+  residual stream   x      fp32 [B*S, D]   (row = image-major token index, CLS first)
+  GEMM operands     *16    fp16, row-major, produced by the LayerNorm / previous GEMM epilogue
+  QKV               qkv16  fp16 [B*S, 3D]  (q | k | v column blocks, head h at columns h*dh inside a block)
+  attention probs   fp16 [B*H, S, Sp]      (Sp = S rounded up to 8 so rows are 16-byte aligned for TMA)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .params import ParamLayout
+from .synth import OwlConfig
+
+
+def _box_bias(cfg: OwlConfig, device) -> torch.Tensor:
+    """HF:1097-1130 compute_box_bias: a constant of the grid size (evaluated once, on the host, in fp32)."""
+    g = cfg.grid
+    xs = torch.arange(1, g + 1, dtype=torch.float32)
+    xx, yy = torch.meshgrid(xs, xs, indexing="xy")
+    coords = torch.stack((xx, yy), dim=-1)
+    coords[..., 0] /= g
+    coords[..., 1] /= g
+    coords = coords.view(-1, 2).clip(0.0, 1.0)
+    coord_bias = torch.log(coords + 1e-4) - torch.log1p(-coords + 1e-4)
+    size = torch.full_like(coord_bias, 1.0)
+    size[..., 0] /= g
+    size[..., 1] /= g
+    size_bias = torch.log(size + 1e-4) - torch.log1p(-size + 1e-4)
+    return torch.cat([coord_bias, size_bias], dim=-1).contiguous().to(device)
+
+
+class Workspace:
+    """All activation buffers for one batch size (allocated once, reused every step)."""
+
+    def __init__(self, cfg: OwlConfig, B: int, device, train: bool):
+        S, P, D, F, E, H = cfg.tokens, cfg.patches, cfg.hidden, cfg.ff, cfg.embed, cfg.heads
+        Q, C = cfg.n_queries, cfg.n_classes
+        f16, f32 = torch.float16, torch.float32
+        self.B = B
+        self.Kp = (3 * cfg.patch_size ** 2 + 7) // 8 * 8
+        self.Sp = (S + 7) // 8 * 8
+
+        def z(shape, dt):
+            return torch.zeros(shape, dtype=dt, device=device)
+
+        self.patches16 = z((B * P, self.Kp), f16)
+        self.emb = z((B * S, D), f32)
+        self.x = z((B * S, D), f32)          # residual stream (input of the last layer after the loop)
+        self.x_mid = z((B * S, D), f32)      # last layer: after attention
+        self.x_out = z((B * S, D), f32)      # last layer: after MLP
+        self.h1 = z((B * S, D), f16)         # LN1 output (kept for the last layer's wgrad)
+        self.h2 = z((B * S, D), f16)         # LN2 output
+        self.qkv = z((B * S, 3 * D), f16)
+        self.probs = z((B * H, S, self.Sp), f16)
+        self.ctx = z((B * S, D), f16)
+        self.m = z((B * S, F), f16)
+        self.mpre = z((B * S, F), f16)
+        self.ecls = z((B, D), f32)
+        self.feats = z((B * P, D), f16)
+        self.e32 = z((B * P, E), f32)
+        self.en16 = z((B * P, E), f16)
+        self.qn16 = z((Q, E), f16)
+        self.argmax = z((B * P, C), torch.uint8)
+        self.bh0 = z((B * P, D), f16)
+        self.bh0pre = z((B * P, D), f16)
+        self.bh1 = z((B * P, D), f16)
+        self.bh1pre = z((B * P, D), f16)
+        self.sig = z((B * P, 4), f32)
+
+
+class Engine:
+    def __init__(self, cfg: OwlConfig, layout: ParamLayout, flat32: torch.Tensor):
+        assert flat32.is_cuda and flat32.dtype == torch.float32 and flat32.numel() == layout.total
+        assert cfg.hidden % 128 == 0 and cfg.embed % 128 == 0 and cfg.head_dim == 64, \
+            "kernels are written for hidden/embed multiples of 128 and 64-wide heads"
+        self.cfg, self.layout = cfg, layout
+        self.flat32 = flat32
+        self.device = flat32.device
+        self.flat16 = torch.zeros(layout.total, dtype=torch.float16, device=self.device)
+        self.Kp = (3 * cfg.patch_size ** 2 + 7) // 8 * 8
+        self.patch_w16 = torch.zeros((cfg.hidden, self.Kp), dtype=torch.float16, device=self.device)
+        self.box_bias = _box_bias(cfg, self.device)
+        self._ws: Dict[int, Workspace] = {}
+        self._shadow_version = None
+        self.refresh_shadow()
+
+    # ------------------------------------------------------------------ parameters
+    def p32(self, name: str) -> torch.Tensor:
+        return self.layout.view(self.flat32, name)
+
+    def p16(self, name: str) -> torch.Tensor:
+        return self.layout.view(self.flat16, name)
+
+    def refresh_shadow(self, trainable_only: bool = False) -> None:
+        """fp32 master -> fp16 GEMM operands (owl_cast_f16).  Cheap: 85 us for all of B/32, 8 us trainable."""
+        lo = self.layout.train_begin if trainable_only else 0
+        ops.cast_f16(self.flat32[lo:], self.flat16[lo:])
+        if not trainable_only:
+            K = 3 * self.cfg.patch_size ** 2
+            w = self.p16("backbone.embeddings.patch_embedding.weight").view(self.cfg.hidden, K)
+            if self.Kp == K:
+                self.patch_w16 = w
+            else:
+                self.patch_w16[:, :K].copy_(w)
+        self._shadow_version = self.flat32._version
+
+    def sync_shadow(self) -> None:
+        if self.flat32._version != self._shadow_version:
+            self.refresh_shadow()
+
+    def workspace(self, B: int) -> Workspace:
+        ws = self._ws.get(B)
+        if ws is None:
+            ws = Workspace(self.cfg, B, self.device, True)
+            self._ws[B] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def _attention(self, ws: Workspace, B: int) -> None:
+        cfg = self.cfg
+        S, D, H, dh, Sp = cfg.tokens, cfg.hidden, cfg.heads, cfg.head_dim, ws.Sp
+        qkv = ws.qkv
+        # scores = (q k^T) / sqrt(dh)   HF:393-396
+        ops.gemm(qkv, qkv[:, D:], ws.probs, M=S, N=S, K=dh, a_ld=3 * D, b_ld=3 * D, ldo=Sp,
+                 batches_outer=B, heads=H, a_outer_stride=S * 3 * D, b_outer_stride=S * 3 * D,
+                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp,
+                 alpha=dh ** -0.5)
+        ops.softmax_rows_f16(ws.probs, rows=B * H * S, n=S, ld=Sp)                      # HF:398
+        # ctx = P v   HF:401, written straight into [B*S, D] (the transpose/reshape of HF:402-403)
+        ops.gemm(ws.probs, qkv[:, 2 * D:], ws.ctx, M=S, N=dh, K=S, b_mn=True, a_ld=Sp, b_ld=3 * D, ldo=D,
+                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
+                 b_outer_stride=S * 3 * D, b_head_col=dh, o_outer_stride=S * D, o_head_stride=dh)
+
+    def forward(self, image: torch.Tensor, save_for_backward: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """image [B,3,IS,IS] fp32 CUDA -> (pred_boxes [B,P,4] xyxy fp32, pred_sims [B,P,C] fp32)."""
+        cfg, L = self.cfg, self.layout
+        assert image.is_cuda and image.dtype == torch.float32 and image.dim() == 4
+        assert image.shape[1] == 3 and image.shape[2] == cfg.image_size and image.shape[3] == cfg.image_size, \
+            f"expected [B,3,{cfg.image_size},{cfg.image_size}], got {tuple(image.shape)}"
+        image = image.contiguous()
+        B = image.shape[0]
+        S, P, D, F, E = cfg.tokens, cfg.patches, cfg.hidden, cfg.ff, cfg.embed
+        Q, C, eps = cfg.n_queries, cfg.n_classes, cfg.ln_eps
+        self.sync_shadow()
+        ws = self.workspace(B)
+        M, MP = B * S, B * P
+
+        # ---- embeddings HF:334-344 + pre_layernorm HF:768
+        ops.im2col_f16(image, ws.patches16, cfg.patch_size)
+        ops.gemm(ws.patches16, self.patch_w16, ws.emb, M=MP, N=D, K=ws.Kp,
+                 pos=self.p32("backbone.embeddings.position_embedding.weight"), rows_per_img=P)
+        ops.layernorm(ws.emb, self.p32("backbone.pre_layernorm.weight"), self.p32("backbone.pre_layernorm.bias"),
+                      ws.x, rows=M, D=D, eps=eps, cls_emb=self.p32("backbone.embeddings.class_embedding"),
+                      pos0=self.p32("backbone.embeddings.position_embedding.weight"), tokens=S)
+
+        # ---- encoder HF:490-511
+        for i in range(cfg.layers):
+            p = f"backbone.encoder.layers.{i}."
+            last = i == cfg.layers - 1
+            x_in = ws.x
+            x_mid = ws.x_mid if last else ws.x
+            x_out = ws.x_out if last else ws.x
+            lo, hi = L.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight")
+            wqkv = self.flat16[lo:hi].view(3 * D, D)
+            lo, hi = L.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias")
+            bqkv = self.flat32[lo:hi]
+            ops.layernorm(x_in, self.p32(p + "layer_norm1.weight"), self.p32(p + "layer_norm1.bias"), ws.h1,
+                          rows=M, D=D, eps=eps)
+            ops.gemm(ws.h1, wqkv, ws.qkv, M=M, N=3 * D, K=D, bias=bqkv)
+            self._attention(ws, B)
+            ops.gemm(ws.ctx, self.p16(p + "self_attn.out_proj.weight"), x_mid, M=M, N=D, K=D,
+                     bias=self.p32(p + "self_attn.out_proj.bias"), resid=x_in)
+            ops.layernorm(x_mid, self.p32(p + "layer_norm2.weight"), self.p32(p + "layer_norm2.bias"), ws.h2,
+                          rows=M, D=D, eps=eps)
+            ops.gemm(ws.h2, self.p16(p + "mlp.fc1.weight"), ws.m, M=M, N=F, K=D, bias=self.p32(p + "mlp.fc1.bias"),
+                     act="quick_gelu", pre_out=ws.mpre if (last and save_for_backward) else None)
+            ops.gemm(ws.m, self.p16(p + "mlp.fc2.weight"), x_out, M=M, N=D, K=F, bias=self.p32(p + "mlp.fc2.bias"),
+                     resid=x_mid)
+
+        # ---- reference src/models.py:80-86: post LN (all tokens) x CLS, second LN
+        g1, b1 = self.p32("backbone.post_layernorm.weight"), self.p32("backbone.post_layernorm.bias")
+        ops.layernorm(ws.x_out, g1, b1, ws.ecls, rows=B, D=D, eps=eps, x_stride=S * D)
+        ops.post_fuse(ws.x_out, ws.ecls, g1, b1, self.p32("post_post_layernorm.weight"),
+                      self.p32("post_post_layernorm.bias"), ws.feats, B=B, P=P, D=D, eps=eps)
+
+        # ---- class head, reference src/models.py:24-38
+        sims = torch.empty((B, P, C), dtype=torch.float32, device=self.device)
+        ops.gemm(ws.feats, self.p16("class_predictor.dense0.weight"), ws.e32, M=MP, N=E, K=D,
+                 bias=self.p32("class_predictor.dense0.bias"))
+        ops.rownorm_f16(ws.e32, ws.en16, rows=MP, E=E, query_mode=False)
+        ops.rownorm_f16(self.p32("queries").view(Q, E), ws.qn16, rows=Q, E=E, query_mode=True)
+        ops.gemm(ws.en16, ws.qn16, sims.view(MP, C), M=MP, N=Q, K=E, pool3=True, argmax=ws.argmax)
+
+        # ---- box head, reference src/models.py:65-73 + HF:1019-1025
+        boxes = torch.empty((B, P, 4), dtype=torch.float32, device=self.device)
+        ops.gemm(ws.feats, self.p16("box_head.dense0.weight"), ws.bh0, M=MP, N=D, K=D,
+                 bias=self.p32("box_head.dense0.bias"), act="gelu", pre_out=ws.bh0pre if save_for_backward else None)
+        ops.gemm(ws.bh0, self.p16("box_head.dense1.weight"), ws.bh1, M=MP, N=D, K=D,
+                 bias=self.p32("box_head.dense1.bias"), act="gelu", pre_out=ws.bh1pre if save_for_backward else None)
+        ops.box_tail(ws.bh1, self.p32("box_head.dense2.weight"), self.p32("box_head.dense2.bias"), self.box_bias,
+                     boxes.view(MP, 4), ws.sig, M=MP, P=P, D=D)
+        return boxes, sims

@@ -63,3 +63,109 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.argmax = ptr(argmax)
     check(lib().owl_gemm(ctypes.byref(g), ctypes.c_void_p(stream_ptr())), "owl_gemm")
     return out
+
+
+def _vp(t) -> ctypes.c_void_p:
+    return ctypes.c_void_p(ptr(t))
+
+
+def _sp() -> ctypes.c_void_p:
+    return ctypes.c_void_p(stream_ptr())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    return t
+
+
+def im2col_f16(img: torch.Tensor, patches: torch.Tensor, patch: int) -> torch.Tensor:
+    """HF:336 patch gather: img [B,3,IS,IS] f32 -> patches [B*g*g, ld] f16 (owl_im2col_f16)."""
+    B, _, IS, _ = img.shape
+    _f32(img)
+    assert patches.dtype == torch.float16 and patches.is_cuda
+    check(lib().owl_im2col_f16(_vp(img), _vp(patches), B, IS, patch, ctypes.c_longlong(patches.stride(0)), _sp()),
+          "owl_im2col_f16")
+    return patches
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, *, rows: int, D: int,
+              eps: float, x_stride: Optional[int] = None, y_stride: Optional[int] = None,
+              cls_emb: Optional[torch.Tensor] = None, pos0: Optional[torch.Tensor] = None,
+              tokens: int = 0) -> torch.Tensor:
+    assert x.dtype == torch.float32 and y.dtype in (torch.float16, torch.float32)
+    xs = D if x_stride is None else x_stride
+    ys = D if y_stride is None else y_stride
+    check(lib().owl_layernorm(_vp(x), ctypes.c_longlong(xs), _vp(gamma), _vp(beta), _vp(y), ctypes.c_longlong(ys),
+                              int(y.dtype == torch.float16), rows, D, ctypes.c_float(eps), _vp(cls_emb), _vp(pos0),
+                              tokens, _sp()), "owl_layernorm")
+    return y
+
+
+def post_fuse(x, ecls, g1, b1, g2, b2, feats, *, B: int, P: int, D: int, eps: float):
+    check(lib().owl_post_fuse(_vp(x), _vp(ecls), _vp(g1), _vp(b1), _vp(g2), _vp(b2), _vp(feats), B, P, D,
+                              ctypes.c_float(eps), _sp()), "owl_post_fuse")
+    return feats
+
+
+def rownorm_f16(e: torch.Tensor, out: torch.Tensor, *, rows: int, E: int, query_mode: bool):
+    _f32(e)
+    assert out.dtype == torch.float16
+    check(lib().owl_rownorm_f16(_vp(e), _vp(out), rows, E, int(query_mode), _sp()), "owl_rownorm_f16")
+    return out
+
+
+def box_tail(h16, w, bias, box_bias, boxes, sig, *, M: int, P: int, D: int):
+    check(lib().owl_box_tail(_vp(h16), _vp(w), _vp(bias), _vp(box_bias), _vp(boxes), _vp(sig), M, P, D, _sp()),
+          "owl_box_tail")
+    return boxes
+
+
+def softmax_rows_f16(scores: torch.Tensor, *, rows: int, n: int, ld: int):
+    check(lib().owl_softmax_rows_f16(_vp(scores), ctypes.c_longlong(rows), n, ld, _sp()), "owl_softmax_rows_f16")
+    return scores
+
+
+def cast_f16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
+    _f32(src)
+    assert dst.dtype == torch.float16 and dst.numel() == src.numel()
+    check(lib().owl_cast_f16(_vp(src), _vp(dst), ctypes.c_longlong(src.numel()), ctypes.c_float(scale), _sp()),
+          "owl_cast_f16")
+    return dst
+
+
+# ------------------------------------------------------------------------------------------ matcher + loss
+def matcher_cost(sims, boxes, labels, tboxes, num_targets, costT, status):
+    """reference src/matcher.py:103-131 -> costT [B,Tmax,P] (owl_matcher_cost)."""
+    B, P, C = sims.shape
+    Tmax = labels.shape[1]
+    _f32(sims), _f32(boxes), _f32(tboxes), _f32(costT)
+    assert labels.dtype == torch.int64 and num_targets.dtype == torch.int32 and status.dtype == torch.int32
+    check(lib().owl_matcher_cost(_vp(sims), _vp(boxes), _vp(labels), _vp(tboxes), _vp(num_targets), _vp(costT), B, P,
+                                 C, Tmax, _vp(status), _sp()), "owl_matcher_cost")
+    return costT
+
+
+def lsap(costT, num_targets, match_pred, status):
+    """reference src/matcher.py:135-137 (SciPy LSAP) -> match_pred [B,Tmax] i32 (owl_lsap)."""
+    B, Tmax, P = costT.shape
+    assert match_pred.dtype == torch.int32
+    check(lib().owl_lsap(_vp(costT), _vp(num_targets), B, P, Tmax, _vp(match_pred), _vp(status), _sp()), "owl_lsap")
+    return match_pred
+
+
+def match_loss(sims, boxes, labels, tboxes, num_targets, match_pred, scales, bg_label, *, tc_matched, tc_final,
+               pred_sorted, tgt_sorted, losses_per_image, losses_mean4, dsims_unit, dl1, dgiou):
+    B, P, C = sims.shape
+    Tmax = labels.shape[1]
+    check(lib().owl_match_loss(_vp(sims), _vp(boxes), _vp(labels), _vp(tboxes), _vp(num_targets), _vp(match_pred),
+                               _vp(scales), B, P, C, Tmax, bg_label, _vp(tc_matched), _vp(tc_final),
+                               _vp(pred_sorted), _vp(tgt_sorted), _vp(losses_per_image), _vp(losses_mean4),
+                               _vp(dsims_unit), _vp(dl1), _vp(dgiou), _sp()), "owl_match_loss")
+
+
+def loss_backward(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, bg_label, dsims, dboxes):
+    B, P, C = dsims_unit.shape
+    Tmax = match_pred.shape[1]
+    check(lib().owl_loss_backward(_vp(dsims_unit), _vp(tc_final), _vp(match_pred), _vp(dl1), _vp(dgiou),
+                                  _vp(upstream4), B, P, C, Tmax, bg_label, _vp(dsims), _vp(dboxes), _sp()),
+          "owl_loss_backward")

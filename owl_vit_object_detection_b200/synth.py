@@ -57,7 +57,7 @@ B32 = OwlConfig()
 # OWL-ViT-L/14 @ 840 (our extension, not a reference capability).
 L14 = OwlConfig(image_size=840, patch_size=14, hidden=1024, layers=24, heads=16, ff=4096, embed=768)
 # A tiny configuration for quick unit tests (same structure, every dimension a legal tile multiple).
-TINY = OwlConfig(image_size=128, patch_size=32, hidden=128, layers=2, heads=2, ff=256, embed=64,
+TINY = OwlConfig(image_size=128, patch_size=32, hidden=128, layers=2, heads=2, ff=256, embed=128,
                  n_classes=8)
 
 

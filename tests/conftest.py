@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _bounded_cpu_threads():
+    # the oracle runs thousands of tiny torch CPU ops; on a many-core GPU host the default
+    # (one thread per core) makes each of them slower, not faster
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    yield
