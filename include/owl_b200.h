@@ -50,7 +50,7 @@ typedef struct owl_gemm_args {
   long long b_outer_stride, b_head_stride;
   int a_head_col, b_head_col;               /* column offset per head */
   int split_k;                              /* >= 1; > 1 requires out_mode == 2 */
-  int bn;                                   /* N tile: 0 = auto, else 64 / 128 / 192 / 256 */
+  int bn;                                   /* N tile: 0 = auto, else 64 / 128 / 256 */
   float alpha;
 
   /* epilogue */
@@ -70,6 +70,7 @@ typedef struct owl_gemm_args {
   int rows_per_img;      /* epilogue 1: > 0 maps output row m -> m + m / rows_per_img + 1 */
   int out_mode;          /* epilogue 1: 0 store, 1 accumulate, 2 atomic add */
   uint8_t* argmax;       /* epilogue 2: winning prompt variant [M, N/3] */
+  const float* alpha_dev; /* optional DEVICE scalar multiplied into alpha (gradient un-scaling without a host sync) */
 } owl_gemm_args;
 
 int owl_gemm(const owl_gemm_args* args, void* stream);
@@ -130,6 +131,50 @@ int owl_match_loss(const float* sims, const float* boxes, const long long* label
 int owl_loss_backward(const float* dsims_unit, const long long* tc_final, const int* match_pred, const float* dl1,
                       const float* dgiou, const float* upstream4, int B, int P, int C, int Tmax, int bg_label,
                       float* dsims, float* dboxes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of the trainable part (autograd of reference main.py:90 under the freeze rule of reference
+ * src/models.py:173-184) and the optimizer step (reference main.py:56-60,91).
+ * Activation gradients are fp16 GEMM operands, pre-multiplied by a power of two S picked on the device:
+ * gscale = {S, 1/S, scratch, scratch} (4 floats).  Kernels that write PARAMETER gradients multiply by 1/S
+ * and ACCUMULATE (atomicAdd) into the flat fp32 gradient buffer, which the caller zeroes once per step.
+ */
+/* S = 2^floor(log2(target / max(|a|, |b|))) clamped to 2^+-24 (1 when the maximum is 0 / not finite). */
+int owl_grad_scale(const float* a, long long na, const float* b, long long nb, float target, float* gscale,
+                   void* stream);
+/* reference src/models.py:36 MaxPool1d(3) backward: dfull [n,3] fp16 = S * dsims routed to the winning variant. */
+int owl_pool3_bwd(const float* dsims, const uint8_t* argmax, const float* gscale, void* dfull_f16, long long n,
+                  void* stream);
+/* reference src/models.py:28-33 backward.  query_mode 0: fp16 out (still scaled); 1: fp32 out += value / S. */
+int owl_rownorm_bwd(const float* e, const float* dy, void* out, int rows, int E, int query_mode,
+                    const float* gscale, void* stream);
+/* reference src/models.py:71-73 + HF:1024 backward: dz [M,4] = S * d(boxes)/d(logits); dpre1 [M,D] fp16 =
+ * (dz W2) * gelu'(pre1); dw2 [4,D] += dz^T h1 / S; db2 [4] += sum dz / S. */
+int owl_box_tail_bwd(const float* dboxes, const float* sig, const float* w2, const void* pre1_f16,
+                     const void* h1_f16, const float* gscale, float* dz, void* dpre1_f16, float* dw2, float* db2,
+                     int M, int D, void* stream);
+/* bias gradients: out[n] += (gscale ? gscale[1] : 1) * sum_m x[m, n]   (x fp16 or fp32, N and ld even). */
+int owl_colsum(const void* x, int is_f16, long long ld, int M, int N, const float* gscale, float* out, void* stream);
+/* HF:398 softmax backward: dS = P * (dP - sum(P dP)) * scale.  P fp16, dP fp32 (the subtraction cancels most of
+ * its magnitude), dS fp16; all [rows, ld] with n <= 1024 valid columns. */
+int owl_softmax_bwd_f16(const void* probs_f16, const float* dprobs_f32, void* dscores_f16, long long rows, int n,
+                        int ld, float scale, void* stream);
+/* LayerNorm backward (HF:498,507; reference src/models.py:80): dx = dx_add + LN'(dy) (dx may be NULL when only the
+ * parameter gradients are needed); dgamma / dbeta += 1/S * sums. */
+int owl_layernorm_bwd(const float* x, long long x_stride, const float* dy, long long dy_stride, const float* gamma,
+                      const float* dx_add, float* dx, long long dx_stride, float* dgamma, float* dbeta, int rows,
+                      int D, float eps, const float* gscale, void* stream);
+/* backward of owl_post_fuse: dx rows of the patch tokens, dcl [B,D] += (scaled), LayerNorm parameter grads += . */
+int owl_post_fuse_bwd(const float* x, const float* ecls, const float* g1, const float* b1, const float* g2,
+                      const float* dfeats, float* dx, float* dcl, float* dg1, float* db1, float* dg2, float* db2,
+                      int B, int P, int D, float eps, const float* gscale, void* stream);
+/* torch.optim.AdamW step (reference main.py:56-60,91) over a flat range; also refreshes the fp16 GEMM shadow.
+ * state = 4 device floats {step count, 1 - beta1^step, sqrt(1 - beta2^step), unused}, zero-initialised by the
+ * caller and advanced on the device (so a captured CUDA graph replays correctly).  grad_mul folds the
+ * 1/world_size of the gradient all-reduce. */
+int owl_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_f16, long long n,
+              float lr, float beta1, float beta2, float eps, float weight_decay, float* state, float grad_mul,
+              void* stream);
 
 #ifdef __cplusplus
 }

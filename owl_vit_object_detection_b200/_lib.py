@@ -38,6 +38,7 @@ class GemmArgs(ctypes.Structure):
         ("resid", c_void_p), ("ldr", c_ll),
         ("pos", c_void_p), ("rows_per_img", c_int), ("out_mode", c_int),
         ("argmax", c_void_p),
+        ("alpha_dev", c_void_p),
     ]
 
 

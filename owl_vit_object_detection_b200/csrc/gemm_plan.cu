@@ -3,13 +3,13 @@
 namespace owl {
 
 static int pick_bn(int M, int N, int G, int split_k, int epilogue, bool b_mn) {
-  if (epilogue == 2) return N <= 256 ? 256 : 192;
+  if (epilogue == 2) return 256;
   const int sms = num_sms();
   const int mb = (M + GEMM_BM - 1) / GEMM_BM;
   int best = 0;
   double best_cost = 0;
-  const int cands[4] = {256, 192, 128, 64};
-  for (int c = 0; c < 4; ++c) {
+  const int cands[3] = {256, 128, 64};
+  for (int c = 0; c < 3; ++c) {
     const int bn = cands[c];
     if (bn > 64 && bn >= 2 * N && N > 0) continue;  // mostly padding
     const long long tiles = 1LL * mb * ((N + bn - 1) / bn) * G * split_k;
@@ -40,7 +40,11 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   p.epilogue = a.epilogue;
   const int G = a.batches_outer * a.heads;
   p.bn = bn ? bn : pick_bn(a.M, a.N, G, a.split_k, a.epilogue, p.b_mn);
-  OWL_CHECK_ARG(p.bn == 64 || p.bn == 128 || p.bn == 192 || p.bn == 256, "gemm: N tile %d not supported", p.bn);
+  OWL_CHECK_ARG(p.bn == 64 || p.bn == 128 || p.bn == 256, "gemm: N tile %d not supported", p.bn);
+  OWL_CHECK_ARG(a.epilogue != 2 || a.N <= 256, "gemm: pool3 epilogue supports N <= 256 (got %d)", a.N);
+  OWL_CHECK_ARG(!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  OWL_CHECK_ARG(!((a.act == 3 || a.act == 4) && a.pre_out), "gemm: act' epilogues cannot also save pre_out");
+  OWL_CHECK_ARG(a.act >= 0 && a.act <= 4 && (a.act == 0 || a.epilogue == 0), "gemm: act %d needs the fp16 epilogue", a.act);
 
   // The third tensor-map dimension enumerates (outer, head) with a common stride when that is
   // expressible; per-head column offsets cover heads packed inside a row (QKV buffer).
@@ -84,21 +88,28 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
 
   const float alpha = a.alpha == 0.0f ? 1.0f : a.alpha;
   if (a.epilogue == 0) {
-    EpiF16::Params& e = p.p16;
+    EpiF16Params& e = p.p16;
+    p.act = a.act;
     e.out = static_cast<__half*>(a.out);
     e.pre_out = static_cast<__half*>(a.pre_out);
     e.bias = a.bias;
     e.dact_src = static_cast<const __half*>(a.act_src);
     e.ldo = static_cast<int>(a.ldo); e.ld_pre = static_cast<int>(a.ld_pre); e.ld_dact = static_cast<int>(a.ld_act_src);
     e.o_sb = a.o_outer_stride; e.o_sh = a.o_head_stride; e.H = a.heads;
-    e.act = a.act; e.alpha = alpha;
+    e.alpha = alpha; e.alpha_dev = a.alpha_dev;
+    auto al16 = [](const void* q, long long ld) { return !q || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld * 2) % 16 == 0); };
+    e.vec_ok = al16(a.out, a.ldo) && al16(a.pre_out, a.ld_pre) && al16(a.act_src, a.ld_act_src) &&
+               (a.o_outer_stride * 2) % 16 == 0 && (a.o_head_stride * 2) % 16 == 0;
   } else if (a.epilogue == 1) {
     EpiF32::Params& e = p.p32;
     e.out = static_cast<float*>(a.out);
     e.bias = a.bias; e.resid = a.resid; e.pos = a.pos;
     e.ldo = static_cast<int>(a.ldo); e.ldr = static_cast<int>(a.ldr);
     e.o_sb = a.o_outer_stride; e.o_sh = a.o_head_stride; e.H = a.heads;
-    e.mode = a.out_mode; e.rows_per_img = a.rows_per_img; e.alpha = alpha;
+    e.mode = a.out_mode; e.rows_per_img = a.rows_per_img; e.alpha = alpha; e.alpha_dev = a.alpha_dev;
+    auto al32 = [](const void* q, long long ld) { return !q || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld * 4) % 16 == 0); };
+    e.vec_ok = al32(a.out, a.ldo) && al32(a.resid, a.ldr) && al32(a.pos, a.ldo) &&
+               (a.o_outer_stride * 4) % 16 == 0 && (a.o_head_stride * 4) % 16 == 0;
   } else {
     EpiPool3::Params& e = p.pp;
     e.sims = static_cast<float*>(a.out);

@@ -11,7 +11,8 @@ struct GemmPlan {
   int bn;
   int a_mn, b_mn;
   int epilogue;  // 0 f16, 1 f32, 2 pool3
-  EpiF16::Params p16;
+  EpiF16Params p16;
+  int act;
   EpiF32::Params p32;
   EpiPool3::Params pp;
   int grid;
@@ -43,7 +44,6 @@ int gemm_launch_one(const GemmPlan& p, const typename Epi::Params& ep, cudaStrea
   switch (p.bn) {                                                                             \
     case 64:  return gemm_launch_one<64, A_MN, B_MN, EPI>(p, params, s);                      \
     case 128: return gemm_launch_one<128, A_MN, B_MN, EPI>(p, params, s);                     \
-    case 192: return gemm_launch_one<192, A_MN, B_MN, EPI>(p, params, s);                     \
     case 256: return gemm_launch_one<256, A_MN, B_MN, EPI>(p, params, s);                     \
     default: set_error("gemm: unsupported N tile %d", p.bn); return OWL_ERR_UNSUPPORTED;      \
   }

@@ -7,15 +7,17 @@
 // * one elected thread issues tcgen05.mma (128 x BN x 16 per instruction) into a double-buffered
 //   TMEM accumulator (2 x BN columns);
 // * four epilogue warps drain TMEM with tcgen05.ld and apply a fused epilogue functor
-//   (bias / activation / residual / position embedding / max-pool / split-K reduction);
+//   (bias / activation / residual / position embedding / max-pool / split-K reduction); every global
+//   read and write of the epilogue is transposed through a per-warp swizzled shared-memory tile so that
+//   each warp-level access covers whole 128-byte lines;
 // * each operand may be K-major (reduction dim contiguous in memory) or MN-major (row index of the
 //   GEMM contiguous in memory) - the second form is what dgrad (B = W as stored) and wgrad
 //   (A = dY^T, B = X^T as stored) need, so no transposed copies are ever made;
 // * a "batch" dimension g = (outer, head) addresses per-head attention matrices inside the packed
 //   [tokens, 3*hidden] QKV buffer through the tensor map's third coordinate / a column offset.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4, column half = (warp_idx - 2) / 4).
 #pragma once
 #include "ptx.cuh"
 
@@ -23,8 +25,9 @@ namespace owl {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 fp16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+constexpr int GEMM_EPI_WARPS = 8;   // two per TMEM lane quadrant, each draining half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_SMEM_BUDGET = 192 * 1024;
 
 struct GemmShape {
   int M, N, K;       // per-batch logical sizes
@@ -39,8 +42,10 @@ __host__ __device__ constexpr int gemm_stage_bytes(int BN) { return (GEMM_BM + B
 __host__ __device__ constexpr int gemm_num_stages(int BN) {
   return GEMM_SMEM_BUDGET / gemm_stage_bytes(BN) > 8 ? 8 : GEMM_SMEM_BUDGET / gemm_stage_bytes(BN);
 }
+constexpr int GEMM_EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B transposition buffer
 __host__ __device__ constexpr int gemm_smem_bytes(int BN) {
-  return gemm_num_stages(BN) * gemm_stage_bytes(BN) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return gemm_num_stages(BN) * gemm_stage_bytes(BN) + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ +
+         256 /*barriers*/;
 }
 __host__ __device__ constexpr int gemm_tmem_cols(int BN) {
   return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -73,7 +78,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;   // 4 KB per epilogue warp
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
@@ -98,7 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -188,8 +194,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------ epilogue warps
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;     // which half of the tile's columns it drains
+    constexpr int NH = BN / 2;
+    const uint32_t stage_buf = smem_u32(epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int g = t / tiles_per_g;
@@ -205,7 +213,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb0 = ks * kb_per;
       // a split whose K range is empty contributes nothing (can happen when split_k does not divide)
       const bool has_k = kb0 < kb_total;
-      Epi::template run<BN>(ep, taddr, g, m_blk * GEMM_BM + row, n_blk * BN, gs.M, gs.N, has_k);
+      if constexpr (Epi::kSplitColumns) {
+        Epi::template run<NH>(ep, taddr + half * NH, stage_buf, g, m_blk * GEMM_BM + quad * 32, lane,
+                              n_blk * BN + half * NH, gs.M, gs.N, has_k);
+      } else if (half == 0) {
+        Epi::template run<BN>(ep, taddr, stage_buf, g, m_blk * GEMM_BM + quad * 32, lane, n_blk * BN, gs.M, gs.N,
+                              has_k);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -221,9 +235,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // =================================================================== epilogues
-__device__ __forceinline__ float act_qgelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+// activation math: MUFU-based (ex2 / rcp), no IEEE-division slow paths
+__device__ __forceinline__ float act_qgelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float act_qgelu_grad(float x) {
-  const float s = 1.0f / (1.0f + __expf(-1.702f * x));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * x));
   return s + 1.702f * x * s * (1.0f - s);
 }
 __device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -233,83 +248,174 @@ __device__ __forceinline__ float act_gelu_grad(float x) {
 
 enum : int { ACT_NONE = 0, ACT_QGELU = 1, ACT_GELU = 2, ACT_QGELU_GRAD = 3, ACT_GELU_GRAD = 4 };
 
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v, float src) {
+  if constexpr (ACT == ACT_QGELU) return act_qgelu(v);
+  else if constexpr (ACT == ACT_GELU) return act_gelu(v);
+  else if constexpr (ACT == ACT_QGELU_GRAD) return v * act_qgelu_grad(src);
+  else if constexpr (ACT == ACT_GELU_GRAD) return v * act_gelu_grad(src);
+  else return v;
+}
+
+// ---- per-warp transposition tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled with (row & 7).
+// "row phase": thread t owns row t (what tcgen05.ld 32x32b gives).  "line phase": lanes 8r..8r+7 own the
+// eight 16-byte chunks of one row, four rows per access, so global accesses cover whole 128-byte lines.
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// line phase, fp16 tile of 32 rows x 64 columns: global -> staging
+__device__ __forceinline__ void tile_load_f16(const __half* src, long long ld, int row0, int n, int M, int N,
+                                              uint32_t stage, int lane, bool vec_ok) {
+  // N here is min(matrix N, end of this warp's column slice)
+  const int sr = lane >> 3, sc = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + sr, m = row0 + row, col = n + sc * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (m < M && col < N) {
+      const __half* s = src + (long long)m * ld + col;
+      if (vec_ok && col + 8 <= N) {
+        v = *reinterpret_cast<const uint4*>(s);
+      } else {
+        __half t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = (col + j < N) ? s[j] : __float2half(0.f);
+        v = *reinterpret_cast<uint4*>(t);
+      }
+    }
+    sts128(stage_addr(stage, row, sc), v);
+  }
+}
+// line phase, fp16 tile: staging -> global
+__device__ __forceinline__ void tile_store_f16(__half* dst, long long ld, int row0, int n, int M, int N,
+                                               uint32_t stage, int lane, bool vec_ok) {
+  const int sr = lane >> 3, sc = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + sr, m = row0 + row, col = n + sc * 8;
+    if (m < M && col < N) {
+      uint4 v = lds128(stage_addr(stage, row, sc));
+      __half* d = dst + (long long)m * ld + col;
+      if (vec_ok && col + 8 <= N) {
+        *reinterpret_cast<uint4*>(d) = v;
+      } else {
+        const __half* t = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col + j < N) d[j] = t[j];
+      }
+    }
+  }
+}
+
 // fp16 output:  v = alpha*acc + bias[n];  optionally save v (pre-activation) to `pre_out`;
 //               then v = act(v)  or  v *= act'(dact_src[m][n]).
+struct EpiF16Params {
+  __half* out;
+  __half* pre_out;
+  const float* bias;
+  const __half* dact_src;
+  int ldo, ld_pre, ld_dact;
+  long long o_sb, o_sh;  // element offsets per outer batch / head
+  int H;
+  int vec_ok;            // all of out / pre_out / dact_src rows are 16-byte aligned
+  float alpha;
+  const float* alpha_dev;  // optional device scalar multiplied into alpha
+};
+
+template <int ACT>
 struct EpiF16 {
-  struct Params {
-    __half* out;
-    __half* pre_out;
-    const float* bias;
-    const __half* dact_src;
-    int ldo, ld_pre, ld_dact;
-    long long o_sb, o_sh;  // element offsets per outer batch / head
-    int H;
-    int act;
-    float alpha;
-  };
+  using Params = EpiF16Params;
+  static constexpr bool kSplitColumns = true;
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, int g, int m, int n0, int M, int N,
-                                             bool has_k) {
+  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, uint32_t stage, int g, int row0,
+                                             int lane, int n0, int M, int Nfull, bool has_k) {
+    const int N = min(Nfull, n0 + BN);  // this warp's column slice ends here
     const int outer = g / p.H, head = g - outer * p.H;
-    const long long obase = outer * p.o_sb + head * p.o_sh;
+    __half* out = p.out + outer * p.o_sb + head * p.o_sh;
+    const bool vec_ok = p.vec_ok != 0;
+    const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+    constexpr bool kGrad = (ACT == ACT_QGELU_GRAD || ACT == ACT_GELU_GRAD);
+    if (row0 >= M) return;  // warp-uniform: nothing of this warp's 32 rows is inside the matrix
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int n = n0 + c * 32;
+    for (int c = 0; c < (BN + 63) / 64; ++c) {
+      const int n = n0 + c * 64;
       if (n >= N) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(taddr + c * 32, r);
-      tmem_ld_wait();
-      if (m >= M) continue;
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * p.alpha : 0.0f;
-      const int nv = min(32, N - n);
-      if (p.bias) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nv) v[i] += __ldg(p.bias + n + i);
+      if constexpr (kGrad) {
+        tile_load_f16(p.dact_src, p.ld_dact, row0, n, M, N, stage, lane, vec_ok);
+        __syncwarp();
       }
-      if (p.pre_out) {
-        __half* po = p.pre_out + (long long)m * p.ld_pre + n;
+      // pass 0 (only with pre_out): pre-activation values; pass 1: activated values
+#pragma unroll 1
+      for (int pass = (p.pre_out ? 0 : 1); pass < 2; ++pass) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nv) po[i] = __float2half_rn(v[i]);
-      }
-      if (p.act == ACT_QGELU) {
+        for (int h = 0; h < 2; ++h) {
+          if (n + h * 32 >= N || c * 64 + h * 32 >= BN) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 64 + h * 32, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = act_qgelu(v[i]);
-      } else if (p.act == ACT_GELU) {
+          for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * alpha : 0.0f;
+          if (p.bias) {
+            if (n + h * 32 + 32 <= N) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = act_gelu(v[i]);
-      } else if (p.act == ACT_QGELU_GRAD || p.act == ACT_GELU_GRAD) {
-        const __half* ds = p.dact_src + (long long)m * p.ld_dact + n;
+              for (int q = 0; q < 8; ++q) {
+                const float4 b = ldg_f4(p.bias + n + h * 32 + 4 * q);
+                v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+              }
+            } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nv) {
-            const float x = __half2float(ds[i]);
-            v[i] *= (p.act == ACT_QGELU_GRAD) ? act_qgelu_grad(x) : act_gelu_grad(x);
+              for (int i = 0; i < 32; ++i)
+                if (n + h * 32 + i < N) v[i] += __ldg(p.bias + n + h * 32 + i);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t sa = stage_addr(stage, lane, h * 4 + q);
+            if (pass == 1) {
+              if constexpr (kGrad) {
+                const uint4 s = lds128(sa);
+                const __half2* sh = reinterpret_cast<const __half2*>(&s);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(sh[j]);
+                  v[8 * q + 2 * j] = apply_act<ACT>(v[8 * q + 2 * j], f.x);
+                  v[8 * q + 2 * j + 1] = apply_act<ACT>(v[8 * q + 2 * j + 1], f.y);
+                }
+              } else if constexpr (ACT != ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[8 * q + j] = apply_act<ACT>(v[8 * q + j], 0.f);
+              }
+            }
+            uint4 pk;
+            pk.x = pack_h2(v[8 * q + 0], v[8 * q + 1]);
+            pk.y = pack_h2(v[8 * q + 2], v[8 * q + 3]);
+            pk.z = pack_h2(v[8 * q + 4], v[8 * q + 5]);
+            pk.w = pack_h2(v[8 * q + 6], v[8 * q + 7]);
+            sts128(sa, pk);
           }
         }
-      }
-      __half* o = p.out + obase + (long long)m * p.ldo + n;
-      if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 pk;
-          __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
-          __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-          __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-          __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
-          pk.x = *reinterpret_cast<uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          pk.z = *reinterpret_cast<uint32_t*>(&h2);
-          pk.w = *reinterpret_cast<uint32_t*>(&h3);
-          reinterpret_cast<uint4*>(o)[i] = pk;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nv) o[i] = __float2half_rn(v[i]);
+        __syncwarp();
+        if (pass == 0) tile_store_f16(p.pre_out, p.ld_pre, row0, n, M, N, stage, lane, vec_ok);
+        else tile_store_f16(out, p.ldo, row0, n, M, N, stage, lane, vec_ok);
+        __syncwarp();
       }
     }
   }
@@ -319,6 +425,7 @@ struct EpiF16 {
 //   mode 0: out = v      mode 1: out += v      mode 2: atomicAdd(out, v)  (split-K / shared outputs)
 //   rows_per_img > 0 remaps output row m -> m + m / rows_per_img + 1 (patch rows -> token rows, CLS first).
 struct EpiF32 {
+  static constexpr bool kSplitColumns = true;
   struct Params {
     float* out;
     const float* bias;
@@ -329,71 +436,120 @@ struct EpiF32 {
     int H;
     int mode;
     int rows_per_img;
+    int vec_ok;            // out / resid / pos rows are 16-byte aligned
     float alpha;
+    const float* alpha_dev;
   };
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, int g, int m, int n0, int M, int N,
-                                             bool has_k) {
+  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, uint32_t stage, int g, int row0,
+                                             int lane, int n0, int M, int N, bool has_k) {
     const int outer = g / p.H, head = g - outer * p.H;
-    const long long obase = outer * p.o_sb + head * p.o_sh;
-    int mo = m;
-    int prow = 0;
-    if (p.rows_per_img > 0) {
-      const int img = m / p.rows_per_img;
-      prow = m - img * p.rows_per_img + 1;
-      mo = m + img + 1;
-    }
+    float* out = p.out + outer * p.o_sb + head * p.o_sh;
+    const bool vec_ok = p.vec_ok != 0;
+    const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+    if (row0 >= M) return;
+    if (!has_k && p.mode != 0) return;  // an empty K slice adds nothing
+    const bool has_add = p.resid != nullptr || p.pos != nullptr || p.mode == 1;
+    const int sr = lane >> 3, sc = lane & 7;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int n = n0 + c * 32;
       if (n >= N) break;
+      if (has_add) {
+        // line phase: gather resid + pos + old output for the 32 x 32 tile.  All global loads are issued
+        // before the first shared store so that their latencies overlap.
+        float4 acc4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + sr, m = row0 + row, col = n + sc * 4;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < M && col < N) {
+            int mo = m, prow = 0;
+            if (p.rows_per_img > 0) {
+              const int img = m / p.rows_per_img;
+              prow = m - img * p.rows_per_img + 1;
+              mo = m + img + 1;
+            }
+            if (vec_ok && col + 4 <= N) {
+              if (p.resid) { const float4 t = *reinterpret_cast<const float4*>(p.resid + (long long)mo * p.ldr + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+              if (p.pos) { const float4 t = ldg_f4(p.pos + (long long)prow * p.ldo + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+              if (p.mode == 1) { const float4 t = *reinterpret_cast<const float4*>(out + (long long)mo * p.ldo + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            } else {
+              float e[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int j = 0; j < 4; ++j) {
+                if (col + j < N) {
+                  if (p.resid) e[j] += p.resid[(long long)mo * p.ldr + col + j];
+                  if (p.pos) e[j] += __ldg(p.pos + (long long)prow * p.ldo + col + j);
+                  if (p.mode == 1) e[j] += out[(long long)mo * p.ldo + col + j];
+                }
+              }
+              a = make_float4(e[0], e[1], e[2], e[3]);
+            }
+          }
+          acc4[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          sts128(stage_addr(stage, i * 4 + sr, sc), make_uint4(__float_as_uint(acc4[i].x), __float_as_uint(acc4[i].y),
+                                                                __float_as_uint(acc4[i].z), __float_as_uint(acc4[i].w)));
+        __syncwarp();
+      }
+      // row phase
       uint32_t r[32];
       tmem_ld32(taddr + c * 32, r);
       tmem_ld_wait();
-      if (m >= M) continue;
-      if (!has_k && p.mode != 0) continue;
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * p.alpha : 0.0f;
-      const int nv = min(32, N - n);
+      for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * alpha : 0.0f;
       if (p.bias) {
+        if (n + 32 <= N) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nv) v[i] += __ldg(p.bias + n + i);
-      }
-      if (p.resid) {
-        const float* rs = p.resid + (long long)mo * p.ldr + n;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nv) v[i] += rs[i];
-      }
-      if (p.pos) {
-        const float* ps = p.pos + (long long)prow * p.ldo + n;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nv) v[i] += __ldg(ps + i);
-      }
-      float* o = p.out + obase + (long long)mo * p.ldo + n;
-      if (p.mode == 2) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nv) atomicAdd(o + i, v[i]);
-      } else {
-        if (p.mode == 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < nv) v[i] += o[i];
-        }
-        if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = ldg_f4(p.bias + n + 4 * q);
+            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < nv) o[i] = v[i];
+            if (n + i < N) v[i] += __ldg(p.bias + n + i);
         }
       }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t sa = stage_addr(stage, lane, q);
+        if (has_add) {
+          const uint4 a = lds128(sa);
+          v[4 * q] += __uint_as_float(a.x); v[4 * q + 1] += __uint_as_float(a.y);
+          v[4 * q + 2] += __uint_as_float(a.z); v[4 * q + 3] += __uint_as_float(a.w);
+        }
+        sts128(sa, make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                              __float_as_uint(v[4 * q + 3])));
+      }
+      __syncwarp();
+      // line phase: write out
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + sr, m = row0 + row, col = n + sc * 4;
+        if (m < M && col < N) {
+          int mo = m;
+          if (p.rows_per_img > 0) mo = m + m / p.rows_per_img + 1;
+          const uint4 u = lds128(stage_addr(stage, row, sc));
+          float* d = out + (long long)mo * p.ldo + col;
+          const float t[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
+          if (p.mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col + j < N) atomicAdd(d + j, t[j]);
+          } else if (vec_ok && col + 4 <= N) {
+            *reinterpret_cast<float4*>(d) = make_float4(t[0], t[1], t[2], t[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col + j < N) d[j] = t[j];
+          }
+        }
+      }
+      __syncwarp();
     }
   }
 };
@@ -401,15 +557,17 @@ struct EpiF32 {
 // Class-head tail (reference src/models.py:35-36): sims[m][c] = max_{j<3} acc[m][3c + j];
 // also records which prompt variant won (for the backward scatter).
 struct EpiPool3 {
+  static constexpr bool kSplitColumns = false;  // groups of 3 columns do not split at BN / 2
   struct Params {
     float* sims;        // [M, C]
     uint8_t* argmax;    // [M, C]
     int C;
   };
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, int g, int m, int n0, int M, int N,
-                                             bool has_k) {
-    (void)g; (void)has_k;
+  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, uint32_t stage, int g, int row0,
+                                             int lane, int n0, int M, int N, bool has_k) {
+    (void)g; (void)has_k; (void)stage;
+    const int m = row0 + lane;
 #pragma unroll 1
     for (int c = 0; c * 96 < BN; ++c) {
       const int n = n0 + c * 96;

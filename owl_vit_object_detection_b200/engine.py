@@ -82,6 +82,44 @@ class Workspace:
         self.bh1 = z((B * P, D), f16)
         self.bh1pre = z((B * P, D), f16)
         self.sig = z((B * P, 4), f32)
+        self._bw = None
+        self._cfg, self._device = cfg, device
+
+    def backward_buffers(self):
+        """Buffers only the backward pass needs (allocated on first use)."""
+        if self._bw is None:
+            cfg, B, device = self._cfg, self.B, self._device
+            S, P, D, F, E, H = cfg.tokens, cfg.patches, cfg.hidden, cfg.ff, cfg.embed, cfg.heads
+            Q = cfg.n_queries
+            f16, f32 = torch.float16, torch.float32
+
+            def z(shape, dt):
+                return torch.zeros(shape, dtype=dt, device=device)
+
+            class _B:
+                pass
+            b = _B()
+            b.gscale = z((4,), f32)
+            b.dfull = z((B * P, Q), f16)
+            b.den32 = z((B * P, E), f32)
+            b.de16 = z((B * P, E), f16)
+            b.dqn32 = z((Q, E), f32)
+            b.dz = z((B * P, 4), f32)
+            b.dpre1 = z((B * P, D), f16)
+            b.dpre0 = z((B * P, D), f16)
+            b.dfeats = z((B * P, D), f32)
+            b.dx_out = z((B * S, D), f32)
+            b.dx_mid = z((B * S, D), f32)
+            b.dcl = z((B, D), f32)
+            b.g16 = z((B * S, D), f16)
+            b.dmpre = z((B * S, F), f16)
+            b.dh32 = z((B * S, D), f32)
+            b.dctx = z((B * S, D), f16)
+            b.dprobs32 = z((B * H, S, self.Sp), f32)
+            b.dprobs = z((B * H, S, self.Sp), f16)
+            b.dqkv = z((B * S, 3 * D), f16)
+            self._bw = b
+        return self._bw
 
 
 class Engine:
@@ -216,3 +254,118 @@ class Engine:
         ops.box_tail(ws.bh1, self.p32("box_head.dense2.weight"), self.p32("box_head.dense2.bias"), self.box_bias,
                      boxes.view(MP, 4), ws.sig, M=MP, P=P, D=D)
         return boxes, sims
+
+    # ------------------------------------------------------------------ backward (reference freeze policy)
+    def _wgrad(self, dy16: torch.Tensor, x16: torch.Tensor, dw: torch.Tensor, *, rows: int, n_out: int, n_in: int,
+               gscale: torch.Tensor) -> None:
+        """dw [n_out, n_in] += (1/S) dy^T x   (split-K tcgen05 GEMM, both operands read as stored)."""
+        tiles = ((n_out + 127) // 128) * ((n_in + 255) // 256)
+        split = max(1, min(16, 148 // max(tiles, 1), (rows + 511) // 512))
+        ops.gemm(dy16, x16, dw, M=n_out, N=n_in, K=rows, a_mn=True, b_mn=True, a_ld=dy16.stride(0),
+                 b_ld=x16.stride(0), ldo=n_in, split_k=split, out_mode=2, alpha_dev=gscale[1:])
+
+    def backward(self, dsims: torch.Tensor, dboxes: torch.Tensor, grad_flat: torch.Tensor) -> None:
+        """Accumulates d(loss)/d(trainable parameters) into grad_flat (fp32, the trainable tail of the flat
+        layout), given d(loss)/d(pred_sims) [B,P,C] and d(loss)/d(pred_boxes) [B,P,4] of the LAST forward."""
+        cfg, L = self.cfg, self.layout
+        B = dsims.shape[0]
+        ws = self.workspace(B)
+        bw = ws.backward_buffers()
+        S, P, D, F, E, H, dh = cfg.tokens, cfg.patches, cfg.hidden, cfg.ff, cfg.embed, cfg.heads, cfg.head_dim
+        Q, C, eps, Sp = cfg.n_queries, cfg.n_classes, cfg.ln_eps, ws.Sp
+        M, MP = B * S, B * P
+        assert dsims.is_cuda and dsims.dtype == torch.float32 and dsims.shape == (B, P, C)
+        assert dboxes.dtype == torch.float32 and dboxes.shape == (B, P, 4)
+        assert grad_flat.dtype == torch.float32 and grad_flat.numel() == L.n_trainable_padded
+        dsims, dboxes = dsims.contiguous(), dboxes.contiguous()
+        gs = bw.gscale
+
+        def gview(name: str) -> torch.Tensor:
+            o = L.offsets[name] - L.train_begin
+            return grad_flat[o:o + L._numel(name)].view(L.shapes[name])
+
+        def gspan(first: str, last: str) -> torch.Tensor:
+            lo, hi = L.span(first, last)
+            return grad_flat[lo - L.train_begin:hi - L.train_begin]
+
+        ops.grad_scale(dsims, dboxes, gs, target=64.0)
+
+        # ---- box head (reference src/models.py:65-73, HF:1019-1025)
+        ops.box_tail_bwd(dboxes, ws.sig, self.p32("box_head.dense2.weight"), ws.bh1pre, ws.bh1, gs, bw.dz, bw.dpre1,
+                         gview("box_head.dense2.weight"), gview("box_head.dense2.bias"), M=MP, D=D)
+        self._wgrad(bw.dpre1, ws.bh0, gview("box_head.dense1.weight"), rows=MP, n_out=D, n_in=D, gscale=gs)
+        ops.colsum(bw.dpre1, gview("box_head.dense1.bias"), M=MP, N=D, gscale=gs)
+        ops.gemm(bw.dpre1, self.p16("box_head.dense1.weight"), bw.dpre0, M=MP, N=D, K=D, b_mn=True,
+                 act="gelu_grad", act_src=ws.bh0pre)
+        self._wgrad(bw.dpre0, ws.feats, gview("box_head.dense0.weight"), rows=MP, n_out=D, n_in=D, gscale=gs)
+        ops.colsum(bw.dpre0, gview("box_head.dense0.bias"), M=MP, N=D, gscale=gs)
+        ops.gemm(bw.dpre0, self.p16("box_head.dense0.weight"), bw.dfeats, M=MP, N=D, K=D, b_mn=True)
+
+        # ---- class head (reference src/models.py:24-38)
+        ops.pool3_bwd(dsims, ws.argmax, gs, bw.dfull)
+        ops.gemm(bw.dfull, ws.qn16, bw.den32, M=MP, N=E, K=Q, b_mn=True)                      # d(en) = dfull qn
+        bw.dqn32.zero_()
+        ops.gemm(bw.dfull, ws.en16, bw.dqn32, M=Q, N=E, K=MP, a_mn=True, b_mn=True, a_ld=Q, b_ld=E, ldo=E,
+                 split_k=max(1, min(16, (MP + 511) // 512)), out_mode=2)                       # d(qn) = dfull^T en
+        ops.rownorm_bwd(self.p32("queries").view(Q, E), bw.dqn32, gview("queries").view(Q, E), rows=Q, E=E,
+                        query_mode=True, gscale=gs)
+        ops.rownorm_bwd(ws.e32, bw.den32, bw.de16, rows=MP, E=E, query_mode=False, gscale=gs)
+        self._wgrad(bw.de16, ws.feats, gview("class_predictor.dense0.weight"), rows=MP, n_out=E, n_in=D, gscale=gs)
+        ops.colsum(bw.de16, gview("class_predictor.dense0.bias"), M=MP, N=E, gscale=gs)
+        ops.gemm(bw.de16, self.p16("class_predictor.dense0.weight"), bw.dfeats, M=MP, N=D, K=E, b_mn=True,
+                 out_mode=1)                                                                   # dfeats += de Wc
+
+        # ---- reference src/models.py:80-86 backward
+        g1n, b1n = "backbone.post_layernorm.weight", "backbone.post_layernorm.bias"
+        bw.dcl.zero_()
+        ops.post_fuse_bwd(ws.x_out, ws.ecls, self.p32(g1n), self.p32(b1n), self.p32("post_post_layernorm.weight"),
+                          bw.dfeats, bw.dx_out, bw.dcl, gview(g1n), gview(b1n), gview("post_post_layernorm.weight"),
+                          gview("post_post_layernorm.bias"), B=B, P=P, D=D, eps=eps, gscale=gs)
+        ops.layernorm_bwd(ws.x_out, bw.dcl, self.p32(g1n), gview(g1n), gview(b1n), rows=B, D=D, eps=eps, gscale=gs,
+                          dx=bw.dx_out, x_stride=S * D, dx_stride=S * D)                       # CLS rows
+
+        # ---- last encoder layer (HF:490-511), MLP half
+        p = f"backbone.encoder.layers.{cfg.layers - 1}."
+        ops.cast_f16(bw.dx_out, bw.g16)
+        self._wgrad(bw.g16, ws.m, gview(p + "mlp.fc2.weight"), rows=M, n_out=D, n_in=F, gscale=gs)
+        ops.colsum(bw.dx_out, gview(p + "mlp.fc2.bias"), M=M, N=D, gscale=gs)
+        ops.gemm(bw.g16, self.p16(p + "mlp.fc2.weight"), bw.dmpre, M=M, N=F, K=D, b_mn=True,
+                 act="quick_gelu_grad", act_src=ws.mpre)
+        self._wgrad(bw.dmpre, ws.h2, gview(p + "mlp.fc1.weight"), rows=M, n_out=F, n_in=D, gscale=gs)
+        ops.colsum(bw.dmpre, gview(p + "mlp.fc1.bias"), M=M, N=F, gscale=gs)
+        ops.gemm(bw.dmpre, self.p16(p + "mlp.fc1.weight"), bw.dh32, M=M, N=D, K=F, b_mn=True)
+        ops.layernorm_bwd(ws.x_mid, bw.dh32, self.p32(p + "layer_norm2.weight"), gview(p + "layer_norm2.weight"),
+                          gview(p + "layer_norm2.bias"), rows=M, D=D, eps=eps, gscale=gs, dx=bw.dx_mid,
+                          dx_add=bw.dx_out)
+
+        # ---- attention half
+        ops.cast_f16(bw.dx_mid, bw.g16)
+        self._wgrad(bw.g16, ws.ctx, gview(p + "self_attn.out_proj.weight"), rows=M, n_out=D, n_in=D, gscale=gs)
+        ops.colsum(bw.dx_mid, gview(p + "self_attn.out_proj.bias"), M=M, N=D, gscale=gs)
+        ops.gemm(bw.g16, self.p16(p + "self_attn.out_proj.weight"), bw.dctx, M=M, N=D, K=D, b_mn=True)
+        qkv, dqkv = ws.qkv, bw.dqkv
+        # dV = P^T dctx
+        ops.gemm(ws.probs, bw.dctx, dqkv[:, 2 * D:], M=S, N=dh, K=S, a_mn=True, b_mn=True, a_ld=Sp, b_ld=D, ldo=3 * D,
+                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
+                 b_outer_stride=S * D, b_head_col=dh, o_outer_stride=S * 3 * D, o_head_stride=dh)
+        # dP = dctx V^T
+        ops.gemm(bw.dctx, qkv[:, 2 * D:], bw.dprobs32, M=S, N=S, K=dh, a_ld=D, b_ld=3 * D, ldo=Sp,
+                 batches_outer=B, heads=H, a_outer_stride=S * D, b_outer_stride=S * 3 * D,
+                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp)
+        ops.softmax_bwd_f16(ws.probs, bw.dprobs32, bw.dprobs, rows=B * H * S, n=S, ld=Sp, scale=dh ** -0.5)
+        # dQ = dS K
+        ops.gemm(bw.dprobs, qkv[:, D:], dqkv, M=S, N=dh, K=S, b_mn=True, a_ld=Sp, b_ld=3 * D, ldo=3 * D,
+                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
+                 b_outer_stride=S * 3 * D, b_head_col=dh, o_outer_stride=S * 3 * D, o_head_stride=dh)
+        # dK = dS^T Q
+        ops.gemm(bw.dprobs, qkv, dqkv[:, D:], M=S, N=dh, K=S, a_mn=True, b_mn=True, a_ld=Sp, b_ld=3 * D, ldo=3 * D,
+                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
+                 b_outer_stride=S * 3 * D, b_head_col=dh, o_outer_stride=S * 3 * D, o_head_stride=dh)
+        gw = gspan(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * D, D)
+        gb = gspan(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias")
+        self._wgrad(dqkv, ws.h1, gw, rows=M, n_out=3 * D, n_in=D, gscale=gs)
+        ops.colsum(dqkv, gb, M=M, N=3 * D, gscale=gs)
+        lo, hi = L.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight")
+        ops.gemm(dqkv, self.flat16[lo:hi].view(3 * D, D), bw.dh32, M=M, N=D, K=3 * D, b_mn=True)
+        ops.layernorm_bwd(ws.x, bw.dh32, self.p32(p + "layer_norm1.weight"), gview(p + "layer_norm1.weight"),
+                          gview(p + "layer_norm1.bias"), rows=M, D=D, eps=eps, gscale=gs)

@@ -24,7 +24,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          split_k: int = 1, bn: int = 0, alpha: float = 1.0, bias: Optional[torch.Tensor] = None,
          act: str = "none", pre_out: Optional[torch.Tensor] = None, act_src: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None, rows_per_img: int = 0,
-         out_mode: int = 0, argmax: Optional[torch.Tensor] = None, pool3: bool = False) -> torch.Tensor:
+         out_mode: int = 0, argmax: Optional[torch.Tensor] = None, pool3: bool = False,
+         alpha_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = alpha * A @ B^T with a fused epilogue; see `struct owl_gemm_args` in include/owl_b200.h."""
     assert a.dtype == torch.float16 and b.dtype == torch.float16 and a.is_cuda and b.is_cuda
     g = GemmArgs()
@@ -61,6 +62,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.rows_per_img = rows_per_img
     g.out_mode = out_mode
     g.argmax = ptr(argmax)
+    g.alpha_dev = ptr(alpha_dev)
     check(lib().owl_gemm(ctypes.byref(g), ctypes.c_void_p(stream_ptr())), "owl_gemm")
     return out
 
@@ -169,3 +171,75 @@ def loss_backward(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, bg_la
     check(lib().owl_loss_backward(_vp(dsims_unit), _vp(tc_final), _vp(match_pred), _vp(dl1), _vp(dgiou),
                                   _vp(upstream4), B, P, C, Tmax, bg_label, _vp(dsims), _vp(dboxes), _sp()),
           "owl_loss_backward")
+
+
+# ------------------------------------------------------------------------------------------ backward kernels
+def _ll(v: int) -> ctypes.c_longlong:
+    return ctypes.c_longlong(v)
+
+
+def _fl(v: float) -> ctypes.c_float:
+    return ctypes.c_float(v)
+
+
+def grad_scale(a: torch.Tensor, b: Optional[torch.Tensor], gscale: torch.Tensor, target: float = 64.0):
+    assert gscale.dtype == torch.float32 and gscale.numel() >= 4
+    check(lib().owl_grad_scale(_vp(a), _ll(a.numel()), _vp(b), _ll(0 if b is None else b.numel()), _fl(target),
+                               _vp(gscale), _sp()), "owl_grad_scale")
+    return gscale
+
+
+def pool3_bwd(dsims, argmax, gscale, dfull16):
+    check(lib().owl_pool3_bwd(_vp(dsims), _vp(argmax), _vp(gscale), _vp(dfull16), _ll(dsims.numel()), _sp()),
+          "owl_pool3_bwd")
+    return dfull16
+
+
+def rownorm_bwd(e, dy, out, *, rows: int, E: int, query_mode: bool, gscale):
+    assert out.dtype == (torch.float32 if query_mode else torch.float16)
+    check(lib().owl_rownorm_bwd(_vp(e), _vp(dy), _vp(out), rows, E, int(query_mode), _vp(gscale), _sp()),
+          "owl_rownorm_bwd")
+    return out
+
+
+def box_tail_bwd(dboxes, sig, w2, pre1_16, h1_16, gscale, dz, dpre1_16, dw2, db2, *, M: int, D: int):
+    check(lib().owl_box_tail_bwd(_vp(dboxes), _vp(sig), _vp(w2), _vp(pre1_16), _vp(h1_16), _vp(gscale), _vp(dz),
+                                 _vp(dpre1_16), _vp(dw2), _vp(db2), M, D, _sp()), "owl_box_tail_bwd")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, *, M: int, N: int, gscale=None, ld: Optional[int] = None):
+    assert x.dtype in (torch.float16, torch.float32) and out.dtype == torch.float32
+    check(lib().owl_colsum(_vp(x), int(x.dtype == torch.float16), _ll(x.stride(-2) if ld is None else ld), M, N,
+                           _vp(gscale), _vp(out), _sp()), "owl_colsum")
+    return out
+
+
+def softmax_bwd_f16(probs, dprobs32, dscores16, *, rows: int, n: int, ld: int, scale: float):
+    assert dprobs32.dtype == torch.float32 and dscores16.dtype == torch.float16
+    check(lib().owl_softmax_bwd_f16(_vp(probs), _vp(dprobs32), _vp(dscores16), _ll(rows), n, ld, _fl(scale), _sp()),
+          "owl_softmax_bwd_f16")
+    return dscores16
+
+
+def layernorm_bwd(x, dy, gamma, dgamma, dbeta, *, rows: int, D: int, eps: float, gscale=None, dx=None, dx_add=None,
+                  x_stride: Optional[int] = None, dy_stride: Optional[int] = None, dx_stride: Optional[int] = None):
+    check(lib().owl_layernorm_bwd(_vp(x), _ll(D if x_stride is None else x_stride), _vp(dy),
+                                  _ll(D if dy_stride is None else dy_stride), _vp(gamma), _vp(dx_add), _vp(dx),
+                                  _ll(D if dx_stride is None else dx_stride), _vp(dgamma), _vp(dbeta), rows, D,
+                                  _fl(eps), _vp(gscale), _sp()), "owl_layernorm_bwd")
+
+
+def post_fuse_bwd(x, ecls, g1, b1, g2, dfeats, dx, dcl, dg1, db1, dg2, db2, *, B: int, P: int, D: int, eps: float,
+                  gscale):
+    check(lib().owl_post_fuse_bwd(_vp(x), _vp(ecls), _vp(g1), _vp(b1), _vp(g2), _vp(dfeats), _vp(dx), _vp(dcl),
+                                  _vp(dg1), _vp(db1), _vp(dg2), _vp(db2), B, P, D, _fl(eps), _vp(gscale), _sp()),
+          "owl_post_fuse_bwd")
+
+
+def adamw(params, grads, exp_avg, exp_avg_sq, params16, *, lr: float, beta1: float, beta2: float, eps: float,
+          weight_decay: float, state: torch.Tensor, grad_mul: float = 1.0):
+    n = params.numel()
+    assert grads.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    check(lib().owl_adamw(_vp(params), _vp(grads), _vp(exp_avg), _vp(exp_avg_sq), _vp(params16), _ll(n), _fl(lr),
+                          _fl(beta1), _fl(beta2), _fl(eps), _fl(weight_decay), _vp(state), _fl(grad_mul), _sp()),
+          "owl_adamw")

@@ -1,0 +1,112 @@
+"""End-to-end through the reference-facing API (src.models.OwlViT / src.losses.PushPullLoss, the classes
+reference main.py:42-91 drives): forward, loss, backward, optimizer step, CUDA-graph capture, smoke()."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import matcher_oracle as mo  # noqa: E402  (checker only)
+from owl_vit_object_detection_b200 import synth  # noqa: E402
+
+
+def _model(cfg, seed=1):
+    from src.models import OwlViT
+    sd = synth.make_weights(cfg, seed=seed)
+    return OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg).to("cuda"), sd
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
+
+
+def test_train_step_like_reference_main():
+    """reference main.py:74-91 with torch.optim.AdamW over model.parameters(), batch 1, unpadded targets."""
+    from src.losses import PushPullLoss
+    cfg = synth.TINY
+    model, sd = _model(cfg)
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert names == synth.trainable_names(cfg) or set(names) == set(synth.trainable_names(cfg))
+    assert set(model.state_dict().keys()) == set(synth.param_shapes(cfg).keys())
+    crit = PushPullLoss(cfg.n_classes, synth.make_class_scales(cfg).cuda())
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.1)
+    img = synth.make_images(cfg, 1, seed=5).cuda()
+    labels, tboxes, nt = synth.make_targets(cfg, 1, seed=3, max_t=8)
+    t = int(nt[0])
+    model.train()
+    first = None
+    for step in range(3):
+        opt.zero_grad()
+        boxes, _, sims, _ = model(img)
+        losses = crit(sims, labels[:, :t].cuda(), boxes, tboxes[:, :t].cuda())
+        loss = losses["loss_ce"] + losses["loss_bg"] + losses["loss_bbox"] + losses["loss_giou"]
+        loss.backward()
+        if step == 0:
+            ref, _, _ = mo.push_pull_loss(sims.detach().cpu(), boxes.detach().cpu(), [labels[0, :t]], [tboxes[0, :t]],
+                                          cfg.n_classes, synth.make_class_scales(cfg))
+            for k in ref:
+                np.testing.assert_allclose(losses[k].item(), ref[k].item(), rtol=1e-4, atol=1e-6)
+            first = loss.item()
+            g = model._param("box_head.dense0.weight").grad
+            assert g is not None and g.abs().max().item() > 0
+        opt.step()
+    assert loss.item() < first, "three AdamW steps on one image should reduce its loss"
+    crit.check_status()
+
+
+def test_eval_forward_no_grad_and_postprocess():
+    from src.models import PostProcess
+    cfg = synth.TINY
+    model, _ = _model(cfg)
+    model.eval()
+    img = synth.make_images(cfg, 1, seed=6).cuda()
+    with torch.no_grad():
+        boxes, none1, sims, none2 = model(img)
+    assert none1 is None and none2 is None and not boxes.requires_grad
+    assert boxes.shape == (1, cfg.patches, 4) and sims.shape == (1, cfg.patches, cfg.n_classes)
+    b, c, s = PostProcess(confidence_threshold=-1.0, iou_threshold=0.6)(boxes, sims)
+    assert b.shape[0] == 1 and b.shape[2] == 4 and c.shape == s.shape
+
+
+def test_cuda_graph_step_matches_eager():
+    """The whole step (forward, matcher, loss, backward, fused AdamW) is capturable: no syncs, no allocations."""
+    from src.losses import PushPullLoss
+    from src.models import FusedAdamW
+    cfg = synth.TINY
+    B = 2
+    img = synth.make_images(cfg, B, seed=5).cuda()
+    labels, tboxes, nt = [x.cuda() for x in synth.make_targets(cfg, B, seed=3, max_t=8)]
+    scales = synth.make_class_scales(cfg).cuda()
+
+    def build():
+        model, _ = _model(cfg)
+        return model, PushPullLoss(cfg.n_classes, scales), FusedAdamW(model, lr=1e-3, weight_decay=0.1)
+
+    def step(model, crit, opt):
+        opt.zero_grad(set_to_none=False)
+        boxes, _, sims, _ = model(img)
+        l = crit(sims, labels, boxes, tboxes, num_targets=nt)
+        (l["loss_ce"] + l["loss_bg"] + l["loss_bbox"] + l["loss_giou"]).backward()
+        opt.step()
+        return torch.stack([l[k].detach() for k in ("loss_ce", "loss_bg", "loss_bbox", "loss_giou")])
+
+    m1, c1, o1 = build()
+    eager = [step(m1, c1, o1).cpu() for _ in range(4)]
+    m2, c2, o2 = build()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        first = step(m2, c2, o2).cpu()            # warm-up (allocates buffers), counts as step 1
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            out = step(m2, c2, o2)
+    torch.cuda.current_stream().wait_stream(s)
+    got = [first]
+    for _ in range(3):
+        graph.replay()
+        got.append(out.cpu().clone())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(got[0].numpy(), eager[0].numpy(), rtol=1e-5)
+    np.testing.assert_allclose(got[1].numpy(), eager[1].numpy(), rtol=1e-3)
