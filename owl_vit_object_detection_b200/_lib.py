@@ -59,7 +59,12 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
-def check(rc: int, what: str) -> None:
+KERNEL_LAUNCHES = 0   # kernels enqueued through the C ABI by this process (bench.py reports it)
+
+
+def check(rc: int, what: str, kernels: int = 1) -> None:
+    global KERNEL_LAUNCHES
+    KERNEL_LAUNCHES += kernels
     if rc != 0:
         msg = lib().owl_last_error().decode(errors="replace")
         raise OwlError(f"{what} failed (code {rc}): {msg}")

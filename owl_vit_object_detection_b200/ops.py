@@ -162,7 +162,7 @@ def match_loss(sims, boxes, labels, tboxes, num_targets, match_pred, scales, bg_
     check(lib().owl_match_loss(_vp(sims), _vp(boxes), _vp(labels), _vp(tboxes), _vp(num_targets), _vp(match_pred),
                                _vp(scales), B, P, C, Tmax, bg_label, _vp(tc_matched), _vp(tc_final),
                                _vp(pred_sorted), _vp(tgt_sorted), _vp(losses_per_image), _vp(losses_mean4),
-                               _vp(dsims_unit), _vp(dl1), _vp(dgiou), _sp()), "owl_match_loss")
+                               _vp(dsims_unit), _vp(dl1), _vp(dgiou), _sp()), "owl_match_loss", kernels=2)
 
 
 def loss_backward(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, bg_label, dsims, dboxes):
@@ -185,7 +185,7 @@ def _fl(v: float) -> ctypes.c_float:
 def grad_scale(a: torch.Tensor, b: Optional[torch.Tensor], gscale: torch.Tensor, target: float = 64.0):
     assert gscale.dtype == torch.float32 and gscale.numel() >= 4
     check(lib().owl_grad_scale(_vp(a), _ll(a.numel()), _vp(b), _ll(0 if b is None else b.numel()), _fl(target),
-                               _vp(gscale), _sp()), "owl_grad_scale")
+                               _vp(gscale), _sp()), "owl_grad_scale", kernels=2)
     return gscale
 
 
@@ -204,7 +204,7 @@ def rownorm_bwd(e, dy, out, *, rows: int, E: int, query_mode: bool, gscale):
 
 def box_tail_bwd(dboxes, sig, w2, pre1_16, h1_16, gscale, dz, dpre1_16, dw2, db2, *, M: int, D: int):
     check(lib().owl_box_tail_bwd(_vp(dboxes), _vp(sig), _vp(w2), _vp(pre1_16), _vp(h1_16), _vp(gscale), _vp(dz),
-                                 _vp(dpre1_16), _vp(dw2), _vp(db2), M, D, _sp()), "owl_box_tail_bwd")
+                                 _vp(dpre1_16), _vp(dw2), _vp(db2), M, D, _sp()), "owl_box_tail_bwd", kernels=2)
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor, *, M: int, N: int, gscale=None, ld: Optional[int] = None):
@@ -242,4 +242,4 @@ def adamw(params, grads, exp_avg, exp_avg_sq, params16, *, lr: float, beta1: flo
     assert grads.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
     check(lib().owl_adamw(_vp(params), _vp(grads), _vp(exp_avg), _vp(exp_avg_sq), _vp(params16), _ll(n), _fl(lr),
                           _fl(beta1), _fl(beta2), _fl(eps), _fl(weight_decay), _vp(state), _fl(grad_mul), _sp()),
-          "owl_adamw")
+          "owl_adamw", kernels=2)

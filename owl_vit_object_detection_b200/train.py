@@ -1,0 +1,124 @@
+"""`TrainStep` — one fine-tuning step (reference main.py:74-91: zero_grad, forward, PushPullLoss, backward,
+optimizer step) as a replayable CUDA graph, with the data-parallel gradient all-reduce between the backward
+graph and the optimizer graph.
+
+  step.load(images_host, labels, boxes, num_targets)   async H2D into static device buffers (side stream)
+  losses4 = step.run()                                  device tensor [loss_ce, loss_bg, loss_bbox, loss_giou]
+
+CUDA streams and graphs replace a tracing compiler: the ~190 kernels of a step are launched by two graph
+replays; the only host work per step is the NCCL all-reduce call (one flat fp32 buffer).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .loss import PushPullLoss
+from .model import FusedAdamW, OwlViT
+
+
+class TrainStep:
+    def __init__(self, model: OwlViT, criterion: PushPullLoss, optimizer: FusedAdamW, batch: int,
+                 max_targets: int = 100, use_graph: bool = True, n_input_slots: int = 2, group=None):
+        cfg = model.cfg
+        dev = model.flat_params.device
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.batch, self.group, self.use_graph = batch, group, use_graph
+        self.slots = []
+        for _ in range(n_input_slots):
+            self.slots.append(dict(
+                image=torch.zeros((batch, 3, cfg.image_size, cfg.image_size), dtype=torch.float32, device=dev),
+                labels=torch.full((batch, max_targets), -1, dtype=torch.int64, device=dev),
+                boxes=torch.zeros((batch, max_targets, 4), dtype=torch.float32, device=dev),
+                nt=torch.ones((batch,), dtype=torch.int32, device=dev)))
+        self.losses = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(n_input_slots)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.loaded = [torch.cuda.Event() for _ in range(n_input_slots)]
+        self.consumed = [torch.cuda.Event() for _ in range(n_input_slots)]
+        self._fwdbwd = [None] * n_input_slots
+        self._opt_graph = None
+        self._world = 1
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self._world = dist.get_world_size(group)
+        optimizer.grad_mul = 1.0 / self._world
+        self._next_load = 0
+        self._next_run = 0
+
+    # ------------------------------------------------------------------ data
+    def load(self, image, labels, boxes, num_targets, slot: Optional[int] = None) -> int:
+        """Asynchronous copy of one batch (host pinned or device tensors) into an input slot."""
+        if slot is None:
+            slot = self._next_load
+            self._next_load = (self._next_load + 1) % len(self.slots)
+        s = self.slots[slot]
+        self.copy_stream.wait_event(self.consumed[slot])
+        with torch.cuda.stream(self.copy_stream):
+            s["image"].copy_(image, non_blocking=True)
+            s["labels"].copy_(labels, non_blocking=True)
+            s["boxes"].copy_(boxes, non_blocking=True)
+            s["nt"].copy_(num_targets, non_blocking=True)
+            self.loaded[slot].record(self.copy_stream)
+        return slot
+
+    # ------------------------------------------------------------------ the step
+    def _fwd_bwd(self, slot: int) -> None:
+        s = self.slots[slot]
+        self.optimizer.zero_grad(set_to_none=False)
+        boxes, _, sims, _ = self.model(s["image"])
+        l = self.criterion(sims, s["labels"], boxes, s["boxes"], num_targets=s["nt"])
+        (l["loss_ce"] + l["loss_bg"] + l["loss_bbox"] + l["loss_giou"]).backward()
+        self.losses[slot].copy_(torch.stack([l["loss_ce"], l["loss_bg"], l["loss_bbox"], l["loss_giou"]]).detach())
+
+    def _capture(self, fn):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn()                                     # warm-up: allocates workspaces, sets kernel attributes
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                fn()
+        cur.wait_stream(side)
+        return g
+
+    def warmup(self) -> None:
+        """Captures the graphs.  NOTE: the capture warm-ups run real steps on whatever the slots hold."""
+        if not self.use_graph:
+            return
+        state = (self.model.flat_params.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
+                 self.optimizer.state.clone())
+        for i in range(len(self.slots)):
+            if self._fwdbwd[i] is None:
+                self._fwdbwd[i] = self._capture(lambda i=i: self._fwd_bwd(i))
+        if self._opt_graph is None:
+            self._opt_graph = self._capture(self.optimizer.step)
+        # undo the optimizer steps the capture warm-ups made
+        self.model.flat_params.copy_(state[0])
+        self.optimizer.exp_avg.copy_(state[1])
+        self.optimizer.exp_avg_sq.copy_(state[2])
+        self.optimizer.state.copy_(state[3])
+        self.model.engine.refresh_shadow()
+
+    def run(self, slot: Optional[int] = None) -> torch.Tensor:
+        if slot is None:
+            slot = self._next_run
+            self._next_run = (self._next_run + 1) % len(self.slots)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.loaded[slot])
+        if self.use_graph:
+            if self._fwdbwd[slot] is None:
+                self.warmup()
+            self._fwdbwd[slot].replay()
+        else:
+            self._fwd_bwd(slot)
+        self.consumed[slot].record(cur)
+        if self._world > 1:
+            self.model.allreduce_grads(self.group)
+        if self.use_graph:
+            self._opt_graph.replay()
+        else:
+            self.optimizer.step()
+        return self.losses[slot]

@@ -1,0 +1,122 @@
+"""CPU-only checks (no GPU needed): the C-ABI library loads and exports every symbol include/owl_b200.h declares,
+the flat parameter layout, the reference-facing module surface, and the data-parallel gradient all-reduce over
+gloo with world_size 2."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from owl_vit_object_detection_b200 import synth  # noqa: E402
+from owl_vit_object_detection_b200.params import ParamLayout  # noqa: E402
+
+
+def test_cabi_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    from owl_vit_object_detection_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    lib = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "owl_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(owl_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20, names
+    for n in names:
+        assert hasattr(lib, n), f"libowl_b200.so does not export {n}"
+    assert lib.owl_abi_version() == 2
+    # argument validation works without a GPU and reports through owl_last_error
+    assert lib.owl_gemm(None, None) != 0
+    assert b"null" in lib.owl_last_error()
+
+
+def test_layout_groups_trainables_and_qkv():
+    for cfg in (synth.B32, synth.TINY, synth.L14):
+        L = ParamLayout(cfg)
+        train = synth.trainable_names(cfg)
+        assert all(L.offsets[n] >= L.train_begin for n in train)
+        assert all(L.offsets[n] < L.train_begin for n in L.shapes if n not in train)
+        for i in range(cfg.layers):
+            p = f"backbone.encoder.layers.{i}.self_attn."
+            lo, hi = L.span(p + "q_proj.weight", p + "v_proj.weight")
+            assert hi - lo == 3 * cfg.hidden * cfg.hidden
+            assert L.offsets[p + "k_proj.weight"] == lo + cfg.hidden * cfg.hidden
+        assert L.train_begin % 64 == 0 and L.total % 64 == 0
+    L = ParamLayout(synth.B32)
+    assert len(synth.trainable_names(synth.B32)) == 29
+    assert sum(L._numel(n) for n in synth.trainable_names(synth.B32)) == 8_791_812
+
+
+def test_module_surface_matches_reference_names():
+    from src.models import OwlViT
+    cfg = synth.TINY
+    sd = synth.make_weights(cfg, seed=1)
+    model = OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg)
+    assert list(model.state_dict().keys()).sort() == list(synth.param_shapes(cfg).keys()).sort()
+    assert {n for n, p in model.named_parameters() if p.requires_grad} == set(synth.trainable_names(cfg))
+    for n, p in model.named_parameters():
+        assert torch.equal(p.detach(), sd[n]), n
+    # in-place optimizer updates write through to the flat buffer
+    with torch.no_grad():
+        model._param("queries").add_(1.0)
+    assert torch.equal(model.layout.view(model.flat_params, "queries"), sd["queries"] + 1.0)
+    # load_state_dict with reference keys works
+    model.load_state_dict(sd)
+    assert torch.equal(model.layout.view(model.flat_params, "queries"), sd["queries"])
+    # no CPU fallback: the product path fails loudly
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 3, cfg.image_size, cfg.image_size))
+
+
+def test_hf_constructor_path():
+    """`OwlViT(pretrained_model=<HF OwlViTForObjectDetection>, query_bank=...)` like reference src/models.py:171."""
+    from transformers import OwlViTConfig, OwlViTForObjectDetection
+    from src.models import OwlViT
+    hc = OwlViTConfig(vision_config=dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                                         num_attention_heads=2, image_size=128, patch_size=32),
+                      text_config=dict(hidden_size=128, intermediate_size=256, num_hidden_layers=1,
+                                       num_attention_heads=2), projection_dim=128)
+    hf = OwlViTForObjectDetection(hc)
+    q = torch.nn.functional.normalize(torch.randn(1, 24, 128), dim=-1)
+    model = OwlViT(pretrained_model=hf, query_bank=q)
+    assert model.cfg.hidden == 128 and model.cfg.layers == 2 and model.cfg.n_classes == 8
+    w = hf.owlvit.vision_model.encoder.layers[1].mlp.fc1.weight
+    assert torch.equal(model._param("backbone.encoder.layers.1.mlp.fc1.weight").detach(), w.detach())
+    assert torch.equal(model._param("class_predictor.dense0.weight").detach(), hf.class_head.dense0.weight.detach())
+
+
+_DDP_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from owl_vit_object_detection_b200 import synth
+from src.models import OwlViT
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo")
+cfg = synth.TINY
+sd = synth.make_weights(cfg, seed=1)
+model = OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg)
+model._prepare_grads()                                          # what backward() does first: .grad = views
+g = model.flat_grad
+g.copy_(torch.arange(g.numel(), dtype=torch.float32) * (rank + 1))
+model.allreduce_grads()
+expect = torch.arange(g.numel(), dtype=torch.float32) * 3      # ranks 1x + 2x
+assert torch.equal(model.flat_grad, expect), "all-reduce(sum) over the flat gradient buffer"
+p = model._param("box_head.dense2.bias")
+o = model.layout.offsets["box_head.dense2.bias"] - model.layout.train_begin
+assert torch.equal(p.grad, expect[o:o + 4])
+dist.destroy_process_group()
+sys.stdout.write("rank " + str(rank) + " ok\n")
+"""
+
+
+def test_allreduce_flat_grads_gloo_world2(tmp_path):
+    script = tmp_path / "ddp_worker.py"
+    script.write_text(_DDP_WORKER % ROOT)
+    port = 29500 + (os.getpid() % 2000)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2, r.stdout
