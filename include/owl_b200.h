@@ -99,6 +99,11 @@ int owl_box_tail(const void* h_f16, const float* w, const float* bias, const flo
 /* HF:398 softmax over the first n columns of each row of an fp16 [rows, ld] buffer, in place (n <= 1024). */
 int owl_softmax_rows_f16(void* scores_f16, long long rows, int n, int ld, void* stream);
 int owl_cast_f16(const float* src, void* dst_f16, long long n, float scale, void* stream);
+/* HF:379-404 fused attention forward: ctx[b, s, h*64 + d] = softmax(scale * q k^T) v for every (image, head), reading
+ * the packed qkv buffer [B*S, 3*H*64] (q | k | v column blocks) and never materialising the scores (tcgen05: S and O
+ * accumulate in TMEM, P is fed back to the tensor core from TMEM).  head_dim must be 64. */
+int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, int B, int S, int H, int head_dim, float scale,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Matcher + loss (reference src/matcher.py:85-159, src/losses.py:16-116), device-resident.

@@ -170,10 +170,15 @@ class Engine:
         return ws
 
     # ------------------------------------------------------------------ forward
-    def _attention(self, ws: Workspace, B: int) -> None:
+    def _attention(self, ws: Workspace, B: int, keep_probs: bool) -> None:
+        """keep_probs=False: fused tcgen05 attention (scores stay in TMEM).  keep_probs=True (last layer when a
+        backward follows): the probabilities are materialised because dV / dS need them."""
         cfg = self.cfg
         S, D, H, dh, Sp = cfg.tokens, cfg.hidden, cfg.heads, cfg.head_dim, ws.Sp
         qkv = ws.qkv
+        if not keep_probs:
+            ops.flash_attn_fwd(qkv, ws.ctx, B=B, S=S, H=H, head_dim=dh, scale=dh ** -0.5)
+            return
         # scores = (q k^T) / sqrt(dh)   HF:393-396
         ops.gemm(qkv, qkv[:, D:], ws.probs, M=S, N=S, K=dh, a_ld=3 * D, b_ld=3 * D, ldo=Sp,
                  batches_outer=B, heads=H, a_outer_stride=S * 3 * D, b_outer_stride=S * 3 * D,
@@ -221,7 +226,7 @@ class Engine:
             ops.layernorm(x_in, self.p32(p + "layer_norm1.weight"), self.p32(p + "layer_norm1.bias"), ws.h1,
                           rows=M, D=D, eps=eps)
             ops.gemm(ws.h1, wqkv, ws.qkv, M=M, N=3 * D, K=D, bias=bqkv)
-            self._attention(ws, B)
+            self._attention(ws, B, keep_probs=last and save_for_backward)
             ops.gemm(ws.ctx, self.p16(p + "self_attn.out_proj.weight"), x_mid, M=M, N=D, K=D,
                      bias=self.p32(p + "self_attn.out_proj.bias"), resid=x_in)
             ops.layernorm(x_mid, self.p32(p + "layer_norm2.weight"), self.p32(p + "layer_norm2.bias"), ws.h2,

@@ -127,6 +127,13 @@ def softmax_rows_f16(scores: torch.Tensor, *, rows: int, n: int, ld: int):
     return scores
 
 
+def flash_attn_fwd(qkv16: torch.Tensor, ctx16: torch.Tensor, *, B: int, S: int, H: int, head_dim: int, scale: float):
+    assert qkv16.dtype == torch.float16 and ctx16.dtype == torch.float16 and qkv16.is_contiguous()
+    check(lib().owl_flash_attn_fwd(_vp(qkv16), _vp(ctx16), B, S, H, head_dim, ctypes.c_float(scale), _sp()),
+          "owl_flash_attn_fwd")
+    return ctx16
+
+
 def cast_f16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
     _f32(src)
     assert dst.dtype == torch.float16 and dst.numel() == src.numel()
