@@ -71,6 +71,7 @@ typedef struct owl_gemm_args {
   int out_mode;          /* epilogue 1: 0 store, 1 accumulate, 2 atomic add */
   uint8_t* argmax;       /* epilogue 2: winning prompt variant [M, N/3] */
   const float* alpha_dev; /* optional DEVICE scalar multiplied into alpha (gradient un-scaling without a host sync) */
+  int cluster_m;         /* thread-block cluster along M with TMA multicast of the B tile: 0 = auto, 1 = off, 2 = pairs */
 } owl_gemm_args;
 
 int owl_gemm(const owl_gemm_args* args, void* stream);

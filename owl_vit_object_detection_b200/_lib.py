@@ -39,6 +39,7 @@ class GemmArgs(ctypes.Structure):
         ("pos", c_void_p), ("rows_per_img", c_int), ("out_mode", c_int),
         ("argmax", c_void_p),
         ("alpha_dev", c_void_p),
+        ("cluster_m", c_int),
     ]
 
 

@@ -3,11 +3,11 @@
 namespace owl {
 int gemm_launch_kk(const GemmPlan& p, cudaStream_t s) {
   if (p.epilogue == 0) {
-    if (p.act == ACT_NONE) { OWL_GEMM_DISPATCH_BN(false, false, EpiF16<ACT_NONE>, p.p16) }
-    if (p.act == ACT_QGELU) { OWL_GEMM_DISPATCH_BN(false, false, EpiF16<ACT_QGELU>, p.p16) }
+    if (p.act == ACT_NONE) { OWL_GEMM_DISPATCH_BN_CM(false, false, EpiF16<ACT_NONE>, p.p16) }
+    if (p.act == ACT_QGELU) { OWL_GEMM_DISPATCH_BN_CM(false, false, EpiF16<ACT_QGELU>, p.p16) }
     if (p.act == ACT_GELU) { OWL_GEMM_DISPATCH_BN(false, false, EpiF16<ACT_GELU>, p.p16) }
   }
-  if (p.epilogue == 1) { OWL_GEMM_DISPATCH_BN(false, false, EpiF32, p.p32) }
+  if (p.epilogue == 1) { OWL_GEMM_DISPATCH_BN_CM(false, false, EpiF32, p.p32) }
   if (p.epilogue == 2 && p.bn == 256) return gemm_launch_one<256, false, false, EpiPool3>(p, p.pp, s);
   set_error("gemm(kk): unsupported epilogue %d / act %d / tile %d", p.epilogue, p.act, p.bn);
   return OWL_ERR_UNSUPPORTED;

@@ -41,6 +41,23 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   const int G = a.batches_outer * a.heads;
   p.bn = bn ? bn : pick_bn(a.M, a.N, G, a.split_k, a.epilogue, p.b_mn);
   OWL_CHECK_ARG(p.bn == 64 || p.bn == 128 || p.bn == 256, "gemm: N tile %d not supported", p.bn);
+  // 2-CTA clusters (B tile multicast) for the big forward / dgrad GEMMs; args.cluster_m: 0 = auto, 1 = off, 2 = on
+  {
+    const int mb_ = (a.M + GEMM_BM - 1) / GEMM_BM;
+    const bool eligible = !p.a_mn && p.bn >= 128 && a.epilogue != 2 && a.act != 2 && a.act != 4 && mb_ >= 2;
+    const long long tiles_ = 1LL * mb_ * ((a.N + p.bn - 1) / p.bn) * G * a.split_k;
+    if (a.cluster_m == 2) {
+      OWL_CHECK_ARG(eligible, "gemm: cluster_m = 2 is not built for this operand layout / epilogue / tile");
+      p.cm = 2;
+    } else if (a.cluster_m == 0) {
+      // measured on B200: the pair flavour wins on long-K problems (8192^3: 1.31 vs 1.22 PFLOP/s) and loses on the
+      // K <= 3072 layer shapes, whose time goes to the epilogue / L2 traffic rather than the MMA main loop
+      p.cm = (eligible && tiles_ >= 2 * num_sms() && a.K >= 6144) ? 2 : 1;
+    } else {
+      OWL_CHECK_ARG(a.cluster_m == 1, "gemm: cluster_m must be 0, 1 or 2");
+      p.cm = 1;
+    }
+  }
   OWL_CHECK_ARG(a.epilogue != 2 || a.N <= 256, "gemm: pool3 epilogue supports N <= 256 (got %d)", a.N);
   OWL_CHECK_ARG(!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   OWL_CHECK_ARG(!((a.act == 3 || a.act == 4) && a.pre_out), "gemm: act' epilogues cannot also save pre_out");
@@ -82,7 +99,7 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   int rc = build_operand(a.a, p.a_mn, a.M, a.a_ld, a.a_outer_stride, a.a_head_stride, a.a_head_col, GEMM_BM,
                          &p.tmA, &gs.a_col_off, &gs.a_sb, &gs.a_sh);
   if (rc) return rc;
-  rc = build_operand(a.b, p.b_mn, a.N, a.b_ld, a.b_outer_stride, a.b_head_stride, a.b_head_col, p.bn, &p.tmB,
+  rc = build_operand(a.b, p.b_mn, a.N, a.b_ld, a.b_outer_stride, a.b_head_stride, a.b_head_col, p.bn / p.cm, &p.tmB,
                      &gs.b_col_off, &gs.b_sb, &gs.b_sh);
   if (rc) return rc;
 
@@ -116,9 +133,10 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
     e.argmax = a.argmax;
     e.C = a.N / 3;
   }
-  const long long tiles = 1LL * ((a.M + GEMM_BM - 1) / GEMM_BM) * ((a.N + p.bn - 1) / p.bn) * G * a.split_k;
-  const int sms = num_sms();
-  p.grid = static_cast<int>(tiles < sms ? tiles : sms);
+  const long long mbc = ((a.M + GEMM_BM - 1) / GEMM_BM + p.cm - 1) / p.cm;
+  const long long ctiles = mbc * ((a.N + p.bn - 1) / p.bn) * G * a.split_k;   // cluster tiles
+  const long long max_clusters = num_sms() / p.cm;
+  p.grid = static_cast<int>((ctiles < max_clusters ? ctiles : max_clusters) * p.cm);
   return OWL_OK;
 }
 

@@ -9,6 +9,7 @@ struct GemmPlan {
   CUtensorMap tmA, tmB;
   GemmShape gs;
   int bn;
+  int cm;        // CTAs per cluster along M (B tile multicast); 1 = no cluster
   int a_mn, b_mn;
   int epilogue;  // 0 f16, 1 f32, 2 pool3
   EpiF16Params p16;
@@ -27,25 +28,51 @@ int gemm_launch_kk(const GemmPlan& p, cudaStream_t s);
 int gemm_launch_kmn(const GemmPlan& p, cudaStream_t s);
 int gemm_launch_mnmn(const GemmPlan& p, cudaStream_t s);
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1>
 int gemm_launch_one(const GemmPlan& p, const typename Epi::Params& ep, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CM>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN)));
+    OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN / CM)));
     configured = true;
   }
-  kern<<<p.grid, GEMM_THREADS, gemm_smem_bytes(BN), s>>>(p.tmA, p.tmB, p.gs, ep);
+  if constexpr (CM == 1) {
+    kern<<<p.grid, GEMM_THREADS, gemm_smem_bytes(BN / CM), s>>>(p.tmA, p.tmB, p.gs, ep);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = gemm_smem_bytes(BN / CM);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CM;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OWL_CUDA(cudaLaunchKernelEx(&cfg, kern, p.tmA, p.tmB, p.gs, ep));
+  }
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
 
 #define OWL_GEMM_DISPATCH_BN(A_MN, B_MN, EPI, params)                                         \
-  switch (p.bn) {                                                                             \
-    case 64:  return gemm_launch_one<64, A_MN, B_MN, EPI>(p, params, s);                      \
-    case 128: return gemm_launch_one<128, A_MN, B_MN, EPI>(p, params, s);                     \
-    case 256: return gemm_launch_one<256, A_MN, B_MN, EPI>(p, params, s);                     \
-    default: set_error("gemm: unsupported N tile %d", p.bn); return OWL_ERR_UNSUPPORTED;      \
+  switch (p.bn * 8 + p.cm) {                                                                  \
+    case 64 * 8 + 1:  return gemm_launch_one<64, A_MN, B_MN, EPI>(p, params, s);              \
+    case 128 * 8 + 1: return gemm_launch_one<128, A_MN, B_MN, EPI>(p, params, s);             \
+    case 256 * 8 + 1: return gemm_launch_one<256, A_MN, B_MN, EPI>(p, params, s);             \
+    default: set_error("gemm: unsupported N tile %d / cluster %d", p.bn, p.cm); return OWL_ERR_UNSUPPORTED; \
+  }
+// forward / dgrad GEMMs additionally come in a 2-CTA-cluster flavour (B tile multicast)
+#define OWL_GEMM_DISPATCH_BN_CM(A_MN, B_MN, EPI, params)                                      \
+  switch (p.bn * 8 + p.cm) {                                                                  \
+    case 64 * 8 + 1:  return gemm_launch_one<64, A_MN, B_MN, EPI>(p, params, s);              \
+    case 128 * 8 + 1: return gemm_launch_one<128, A_MN, B_MN, EPI>(p, params, s);             \
+    case 256 * 8 + 1: return gemm_launch_one<256, A_MN, B_MN, EPI>(p, params, s);             \
+    case 128 * 8 + 2: return gemm_launch_one<128, A_MN, B_MN, EPI, 2>(p, params, s);          \
+    case 256 * 8 + 2: return gemm_launch_one<256, A_MN, B_MN, EPI, 2>(p, params, s);          \
+    default: set_error("gemm: unsupported N tile %d / cluster %d", p.bn, p.cm); return OWL_ERR_UNSUPPORTED; \
   }
 
 }  // namespace owl

@@ -43,6 +43,7 @@ __host__ __device__ constexpr int gemm_num_stages(int BN) {
   return GEMM_SMEM_BUDGET / gemm_stage_bytes(BN) > 8 ? 8 : GEMM_SMEM_BUDGET / gemm_stage_bytes(BN);
 }
 constexpr int GEMM_EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B transposition buffer
+// BN here is the number of B rows ONE CTA stages (BN / 2 in the pair flavour)
 __host__ __device__ constexpr int gemm_smem_bytes(int BN) {
   return gemm_num_stages(BN) * gemm_stage_bytes(BN) + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ +
          256 /*barriers*/;
@@ -64,14 +65,28 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int k16) {
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
+// CM = 2 selects the CTA-pair flavour (tcgen05 cta_group::2): the two CTAs of a cluster own two consecutive 128-row
+// M tiles of the SAME N tile.  One thread of the leader CTA issues M = 256 MMAs that read each CTA's A tile and each
+// CTA's HALF of the B tile from that CTA's own shared memory, so per CTA both the TMA fill and the tensor-core
+// operand fetch of B are halved.  That matters because a single-CTA 128x256 tile needs 96 B/clk of operand reads
+// plus 96 B/clk of TMA writes against the 128 B/clk shared-memory port (measured: 1.04 PFLOP/s = 63 % of cuBLAS),
+// while the pair needs 64 + 64.
+//   full_bar   leader only: its own arrive.expect_tx(2 x stage bytes) + complete_tx from both CTAs' TMA loads
+//   empty_bar  per CTA, count 1: the leader's tcgen05.commit is multicast to both CTAs
+//   tfull_bar  per CTA, count 1: same multicast commit after the last k-block of a tile
+//   tempty_bar leader only, count 2 x epilogue warps: the peer's epilogue warps arrive remotely
+template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmShape gs, const typename Epi::Params ep) {
-  constexpr int STAGES = gemm_num_stages(BN);
+  static_assert(CM == 1 || CM == 2, "1 = single CTA, 2 = CTA pair (cta_group::2)");
+  static_assert(CM == 1 || !A_MN, "the pair flavour is built for K-major A");
+  static_assert(!B_MN || (BN / 64) % CM == 0, "MN-major B: whole 64-wide chunks per CTA");
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr int BN_CTA = BN / CM;                       // B rows held by one CTA
+  constexpr int B_BYTES = BN_CTA * GEMM_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = gemm_num_stages(BN_CTA);
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN);
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(!B_MN || BN % 64 == 0, "MN-major B tiles are loaded in 64-wide chunks");
@@ -92,8 +107,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nb = (gs.N + BN - 1) / BN;
   const int kb_total = (gs.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_per = (kb_total + gs.split_k - 1) / gs.split_k;
-  const int tiles_per_g = mb * nb * gs.split_k;
+  const int mbc = (mb + CM - 1) / CM;                       // M tiles in units of clusters
+  const int tiles_per_g = mbc * nb * gs.split_k;            // cluster tiles per batch
   const int num_tiles = tiles_per_g * gs.G;
+  const int crank = CM > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = crank == 0;
+  const int cluster_id = blockIdx.x / CM, num_clusters = gridDim.x / CM;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -104,93 +123,125 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * CM);
     }
     fence_barrier_init();
   }
+  if constexpr (CM > 1) cluster_sync_all();   // both CTAs are resident with initialised barriers before pair ops
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CM == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+    else { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
+    // ------------------------------------------------ TMA producer (every CTA fills its own shared memory)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int g = t / tiles_per_g;
         int r = t - g * tiles_per_g;
-        const int ks = r / (mb * nb);
-        r -= ks * (mb * nb);
-        const int m_blk = r / nb, n_blk = r - (r / nb) * nb;
+        const int ks = r / (mbc * nb);
+        r -= ks * (mbc * nb);
+        const int m_blk = (r / nb) * CM + crank, n_blk = r - (r / nb) * nb;
         const int outer = g / gs.H, head = g - outer * gs.H;
         const int a_c = head * gs.a_col_off, a_b = outer * gs.a_sb + head * gs.a_sh;
         const int b_c = head * gs.b_col_off, b_b = outer * gs.b_sb + head * gs.b_sh;
-        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+        const int m0 = m_blk * GEMM_BM;
+        const int n0 = n_blk * BN + crank * BN_CTA;          // this CTA's slice of the B tile
         const int kb0 = ks * kb_per;
         const int kb1 = min(kb0 + kb_per, kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          if constexpr (!A_MN) {
-            tma_load_3d(sa, &tmA, &full_bar[stage], kb * GEMM_BK + a_c, m0, a_b);
-          } else {
+          if constexpr (CM == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_3d(sa, &tmA, &full_bar[stage], kb * GEMM_BK + a_c, m0, a_b);
+            } else {
 #pragma unroll
-            for (int c = 0; c < GEMM_BM / 64; ++c)
-              tma_load_3d(sa + c * 8192, &tmA, &full_bar[stage], m0 + c * 64 + a_c, kb * GEMM_BK, a_b);
-          }
-          if constexpr (!B_MN) {
-            tma_load_3d(sb, &tmB, &full_bar[stage], kb * GEMM_BK + b_c, n0, b_b);
-          } else {
+              for (int c = 0; c < GEMM_BM / 64; ++c)
+                tma_load_3d(sa + c * 8192, &tmA, &full_bar[stage], m0 + c * 64 + a_c, kb * GEMM_BK, a_b);
+            }
+            if constexpr (!B_MN) {
+              tma_load_3d(sb, &tmB, &full_bar[stage], kb * GEMM_BK + b_c, n0, b_b);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_3d(sb + c * 8192, &tmB, &full_bar[stage], n0 + c * 64 + b_c, kb * GEMM_BK, b_b);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_3d(sb + c * 8192, &tmB, &full_bar[stage], n0 + c * 64 + b_c, kb * GEMM_BK, b_b);
+            }
+          } else {
+            // the leader's barrier collects the bytes of both CTAs
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            tma_load_3d_2sm(sa, &tmA, &full_bar[stage], kb * GEMM_BK + a_c, m0, a_b);
+            if constexpr (!B_MN) {
+              tma_load_3d_2sm(sb, &tmB, &full_bar[stage], kb * GEMM_BK + b_c, n0, b_b);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN_CTA / 64; ++c)
+                tma_load_3d_2sm(sb + c * 8192, &tmB, &full_bar[stage], n0 + c * 64 + b_c, kb * GEMM_BK, b_b);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    constexpr uint32_t IDESC = make_idesc_f16(GEMM_BM, BN, A_MN, B_MN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int r = t % tiles_per_g;
-      const int ks = r / (mb * nb);
-      const int kb0 = ks * kb_per;
-      const int kb1 = min(kb0 + kb_per, kb_total);
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ------------------------------------------------ MMA issuer (pair flavour: leader CTA only)
+    if (CM == 1 || leader) {
+      constexpr uint32_t IDESC = make_idesc_f16(GEMM_BM * CM, BN, A_MN, B_MN);
+      // The whole warp walks the loop with warp-uniform state; one elected lane issues.  Descriptors are built once
+      // and advanced by adding to their 14-bit (address >> 4) field: the issue loop must stay far below the
+      // 512 clk a k-block of MMAs takes, or the issuing thread itself becomes the bottleneck.
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t adesc0 = operand_desc<A_MN>(smem_base, 0);
+      const uint64_t bdesc0 = operand_desc<B_MN>(smem_base + A_BYTES, 0);
+      constexpr uint64_t KSTEP_A = (A_MN ? 2048 : 32) >> 4, KSTEP_B = (B_MN ? 2048 : 32) >> 4;
+      constexpr uint64_t STAGE_STEP = STAGE_BYTES >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int r = t % tiles_per_g;
+        const int ks = r / (mbc * nb);
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(kb0 + kb_per, kb_total);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = adesc0 + stage * STAGE_STEP, bd = bdesc0 + stage * STAGE_STEP;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_f16(d_tmem, operand_desc<A_MN>(sa, k), operand_desc<B_MN>(sb, k), IDESC,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              if constexpr (CM == 1)
+                umma_f16(d_tmem, ad + k * KSTEP_A, bd + k * KSTEP_B, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+              else
+                umma_f16_2sm(d_tmem, ad + k * KSTEP_A, bd + k * KSTEP_B, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (of both CTAs in the pair flavour) when these MMAs retire
+            if constexpr (CM == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_2sm(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one_sync()) {
+          if constexpr (CM == 1) umma_commit(&tfull_bar[as]);
+          else umma_commit_2sm(&tfull_bar[as]);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(&tfull_bar[as]);
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------ epilogue warps
@@ -199,14 +250,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NH = BN / 2;
     const uint32_t stage_buf = smem_u32(epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES);
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int g = t / tiles_per_g;
       int r = t - g * tiles_per_g;
-      const int ks = r / (mb * nb);
-      r -= ks * (mb * nb);
-      const int m_blk = r / nb, n_blk = r - (r / nb) * nb;
+      const int ks = r / (mbc * nb);
+      r -= ks * (mbc * nb);
+      const int m_blk = (r / nb) * CM + crank, n_blk = r - (r / nb) * nb;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = m_blk * GEMM_BM + quad * 32;
+      const int ncol0 = n_blk * BN + (Epi::kSplitColumns ? half * NH : 0);
+      // global operands of the epilogue (bias slice, first residual chunk) are fetched BEFORE waiting for the
+      // accumulator, so their latency hides behind the tile's MMAs
+      typename Epi::Pre pre;
+      Epi::template prologue<Epi::kSplitColumns ? NH : BN>(ep, pre, g, row0, lane, ncol0, gs.M, gs.N);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -214,23 +271,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // a split whose K range is empty contributes nothing (can happen when split_k does not divide)
       const bool has_k = kb0 < kb_total;
       if constexpr (Epi::kSplitColumns) {
-        Epi::template run<NH>(ep, taddr + half * NH, stage_buf, g, m_blk * GEMM_BM + quad * 32, lane,
-                              n_blk * BN + half * NH, gs.M, gs.N, has_k);
+        Epi::template run<NH>(ep, pre, taddr + half * NH, stage_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
       } else if (half == 0) {
-        Epi::template run<BN>(ep, taddr, stage_buf, g, m_blk * GEMM_BM + quad * 32, lane, n_blk * BN, gs.M, gs.N,
-                              has_k);
+        Epi::template run<BN>(ep, pre, taddr, stage_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CM == 1) mbar_arrive(&tempty_bar[as]);
+        else mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread owns the accumulator hand-off
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  // no CTA may exit (or free TMEM) while its partner can still touch its shared memory, barriers or TMEM
+  if constexpr (CM > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CM == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    else tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -278,6 +339,30 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// bias slice of one epilogue warp: lane l holds columns ncol0 + 4l .. 4l+3 (zero outside [0, N) or the slice)
+template <int W>
+__device__ __forceinline__ float4 load_bias_slice(const float* bias, int ncol0, int N, int lane) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int c = ncol0 + 4 * lane;
+  if (bias != nullptr && 4 * lane < W && c < N) {
+    if (c + 4 <= N) {
+      b = ldg_f4(bias + c);
+    } else {
+      b.x = __ldg(bias + c);
+      if (c + 1 < N) b.y = __ldg(bias + c + 1);
+      if (c + 2 < N) b.z = __ldg(bias + c + 2);
+    }
+  }
+  return b;
+}
+// v[0..3] += bias columns 4 * src_lane .. + 3 (all lanes must call)
+__device__ __forceinline__ void add_bias4(float* v, const float4& b, int src_lane) {
+  v[0] += __shfl_sync(0xffffffffu, b.x, src_lane);
+  v[1] += __shfl_sync(0xffffffffu, b.y, src_lane);
+  v[2] += __shfl_sync(0xffffffffu, b.z, src_lane);
+  v[3] += __shfl_sync(0xffffffffu, b.w, src_lane);
+}
 
 // line phase, fp16 tile of 32 rows x 64 columns: global -> staging
 __device__ __forceinline__ void tile_load_f16(const __half* src, long long ld, int row0, int n, int M, int N,
@@ -343,9 +428,16 @@ template <int ACT>
 struct EpiF16 {
   using Params = EpiF16Params;
   static constexpr bool kSplitColumns = true;
+  struct Pre { float4 bias; };
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, uint32_t stage, int g, int row0,
-                                             int lane, int n0, int M, int Nfull, bool has_k) {
+  static __device__ __forceinline__ void prologue(const Params& p, Pre& pre, int g, int row0, int lane, int n0, int M,
+                                                  int N) {
+    (void)g; (void)row0; (void)M;
+    pre.bias = load_bias_slice<BN>(p.bias, n0, N, lane);
+  }
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& p, const Pre& pre, uint32_t taddr, uint32_t stage, int g,
+                                             int row0, int lane, int n0, int M, int Nfull, bool has_k) {
     const int N = min(Nfull, n0 + BN);  // this warp's column slice ends here
     const int outer = g / p.H, head = g - outer * p.H;
     __half* out = p.out + outer * p.o_sb + head * p.o_sh;
@@ -374,17 +466,8 @@ struct EpiF16 {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * alpha : 0.0f;
           if (p.bias) {
-            if (n + h * 32 + 32 <= N) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 b = ldg_f4(p.bias + n + h * 32 + 4 * q);
-                v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n + h * 32 + i < N) v[i] += __ldg(p.bias + n + h * 32 + i);
-            }
+            for (int q = 0; q < 8; ++q) add_bias4(v + 4 * q, pre.bias, c * 16 + h * 8 + q);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -440,59 +523,78 @@ struct EpiF32 {
     float alpha;
     const float* alpha_dev;
   };
+  struct Pre { float4 bias; float4 add[8]; };
+  // line phase gather of resid + pos + old output for the 32 x 32 tile at column n (registers only)
+  static __device__ __forceinline__ void load_addend(const Params& p, const float* out, int row0, int n, int M, int N,
+                                                     int lane, float4* acc4) {
+    const bool vec_ok = p.vec_ok != 0;
+    const int sr = lane >> 3, sc = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + sr, m = row0 + row, col = n + sc * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && col < N) {
+        int mo = m, prow = 0;
+        if (p.rows_per_img > 0) {
+          const int img = m / p.rows_per_img;
+          prow = m - img * p.rows_per_img + 1;
+          mo = m + img + 1;
+        }
+        if (vec_ok && col + 4 <= N) {
+          if (p.resid) { const float4 t = *reinterpret_cast<const float4*>(p.resid + (long long)mo * p.ldr + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+          if (p.pos) { const float4 t = ldg_f4(p.pos + (long long)prow * p.ldo + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+          if (p.mode == 1) { const float4 t = *reinterpret_cast<const float4*>(out + (long long)mo * p.ldo + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        } else {
+          float e[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < 4; ++j) {
+            if (col + j < N) {
+              if (p.resid) e[j] += p.resid[(long long)mo * p.ldr + col + j];
+              if (p.pos) e[j] += __ldg(p.pos + (long long)prow * p.ldo + col + j);
+              if (p.mode == 1) e[j] += out[(long long)mo * p.ldo + col + j];
+            }
+          }
+          a = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+      acc4[i] = a;
+    }
+  }
+  static __device__ __forceinline__ bool has_addend(const Params& p) {
+    return p.resid != nullptr || p.pos != nullptr || p.mode == 1;
+  }
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, uint32_t stage, int g, int row0,
-                                             int lane, int n0, int M, int N, bool has_k) {
+  static __device__ __forceinline__ void prologue(const Params& p, Pre& pre, int g, int row0, int lane, int n0, int M,
+                                                  int N) {
+    pre.bias = load_bias_slice<BN>(p.bias, n0, N, lane);
+    if (has_addend(p) && row0 < M && n0 < N) {
+      const int outer = g / p.H, head = g - outer * p.H;
+      load_addend(p, p.out + outer * p.o_sb + head * p.o_sh, row0, n0, M, N, lane, pre.add);
+    }
+  }
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& p, Pre& pre, uint32_t taddr, uint32_t stage, int g,
+                                             int row0, int lane, int n0, int M, int N, bool has_k) {
     const int outer = g / p.H, head = g - outer * p.H;
     float* out = p.out + outer * p.o_sb + head * p.o_sh;
     const bool vec_ok = p.vec_ok != 0;
     const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
     if (row0 >= M) return;
     if (!has_k && p.mode != 0) return;  // an empty K slice adds nothing
-    const bool has_add = p.resid != nullptr || p.pos != nullptr || p.mode == 1;
+    const bool has_add = has_addend(p);
     const int sr = lane >> 3, sc = lane & 7;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int n = n0 + c * 32;
       if (n >= N) break;
       if (has_add) {
-        // line phase: gather resid + pos + old output for the 32 x 32 tile.  All global loads are issued
-        // before the first shared store so that their latencies overlap.
-        float4 acc4[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + sr, m = row0 + row, col = n + sc * 4;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < M && col < N) {
-            int mo = m, prow = 0;
-            if (p.rows_per_img > 0) {
-              const int img = m / p.rows_per_img;
-              prow = m - img * p.rows_per_img + 1;
-              mo = m + img + 1;
-            }
-            if (vec_ok && col + 4 <= N) {
-              if (p.resid) { const float4 t = *reinterpret_cast<const float4*>(p.resid + (long long)mo * p.ldr + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-              if (p.pos) { const float4 t = ldg_f4(p.pos + (long long)prow * p.ldo + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-              if (p.mode == 1) { const float4 t = *reinterpret_cast<const float4*>(out + (long long)mo * p.ldo + col); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-            } else {
-              float e[4] = {0.f, 0.f, 0.f, 0.f};
-              for (int j = 0; j < 4; ++j) {
-                if (col + j < N) {
-                  if (p.resid) e[j] += p.resid[(long long)mo * p.ldr + col + j];
-                  if (p.pos) e[j] += __ldg(p.pos + (long long)prow * p.ldo + col + j);
-                  if (p.mode == 1) e[j] += out[(long long)mo * p.ldo + col + j];
-                }
-              }
-              a = make_float4(e[0], e[1], e[2], e[3]);
-            }
-          }
-          acc4[i] = a;
-        }
+        // the addend of this chunk was fetched one chunk (or one tile prologue) ago: park it in the staging tile
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          sts128(stage_addr(stage, i * 4 + sr, sc), make_uint4(__float_as_uint(acc4[i].x), __float_as_uint(acc4[i].y),
-                                                                __float_as_uint(acc4[i].z), __float_as_uint(acc4[i].w)));
+          sts128(stage_addr(stage, i * 4 + sr, sc), make_uint4(__float_as_uint(pre.add[i].x), __float_as_uint(pre.add[i].y),
+                                                                __float_as_uint(pre.add[i].z), __float_as_uint(pre.add[i].w)));
         __syncwarp();
+        // ... and start fetching the next chunk's addend now, so its latency overlaps this chunk's row phase
+        if (c + 1 < BN / 32 && n + 32 < N) load_addend(p, out, row0, n + 32, M, N, lane, pre.add);
       }
       // row phase
       uint32_t r[32];
@@ -502,17 +604,8 @@ struct EpiF32 {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * alpha : 0.0f;
       if (p.bias) {
-        if (n + 32 <= N) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 b = ldg_f4(p.bias + n + 4 * q);
-            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n + i < N) v[i] += __ldg(p.bias + n + i);
-        }
+        for (int q = 0; q < 8; ++q) add_bias4(v + 4 * q, pre.bias, c * 8 + q);
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -563,9 +656,12 @@ struct EpiPool3 {
     uint8_t* argmax;    // [M, C]
     int C;
   };
+  struct Pre {};
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, uint32_t stage, int g, int row0,
-                                             int lane, int n0, int M, int N, bool has_k) {
+  static __device__ __forceinline__ void prologue(const Params&, Pre&, int, int, int, int, int, int) {}
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& p, const Pre&, uint32_t taddr, uint32_t stage, int g,
+                                             int row0, int lane, int n0, int M, int N, bool has_k) {
     (void)g; (void)has_k; (void)stage;
     const int m = row0 + lane;
 #pragma unroll 1

@@ -244,6 +244,114 @@ lsap_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets
   for (int t = lane; t < Tmax; t += 32) match_pred[1LL * b * Tmax + t] = t < nr ? col4row[t] : -1;
 }
 
+// Same solver, one CTA per image: used when the batch is too small to fill the GPU with one warp per image
+// (a training step has 16 images; the slowest image sets the latency).  Every scan over the remaining columns is
+// spread over NT threads; candidates are combined with the same associative tie rule.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+lsap_block_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets, int P, int Tmax,
+                  int* __restrict__ match_pred /*[B,Tmax]*/, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  constexpr int NW = NT / 32;
+  __shared__ Cand wbest[NW];
+  __shared__ int s_sink, s_i;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const int Tpad = (Tmax + 4) & ~3;
+  double* spc = reinterpret_cast<double*>(lsm);
+  double* v = spc + P;
+  double* u = v + P;
+  short* path = reinterpret_cast<short*>(u + Tpad);
+  short* row4col = path + P;
+  short* remaining = row4col + P;
+  short* col4row = remaining + P;
+  short* sr_list = col4row + Tpad;
+  short* sc_list = sr_list + Tpad + 4;
+
+  const int nr = num_targets[b], nc = P;
+  const float* cost = costT + 1LL * b * Tmax * P;
+  for (int j = tid; j < nc; j += NT) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
+  for (int i = tid; i < nr; i += NT) { u[i] = 0.0; col4row[i] = -1; }
+  __syncthreads();
+
+  for (int cur = 0; cur < nr; ++cur) {
+    for (int j = tid; j < nc; j += NT) { spc[j] = CUDART_INF; remaining[j] = static_cast<short>(nc - 1 - j); }
+    int num_remaining = nc, n_sr = 0, n_sc = 0;
+    double min_val = 0.0;
+    int i = cur, sink = -1;
+    __syncthreads();
+    while (sink < 0) {
+      if (tid == 0) sr_list[n_sr] = static_cast<short>(i);
+      ++n_sr;
+      const double ui = u[i];
+      const float* crow = cost + 1LL * i * nc;
+      Cand best = {0.0, 0, -1};
+      for (int it = tid; it < num_remaining; it += NT) {
+        const int j = remaining[it];
+        const double r = ((min_val + static_cast<double>(__ldg(crow + j))) - ui) - v[j];
+        double sj = spc[j];
+        if (r < sj) { path[j] = static_cast<short>(i); spc[j] = r; sj = r; }
+        const Cand c = {sj, row4col[j] == -1 ? 1 : 0, it};
+        best = cand_combine(best, c);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Cand other;
+        other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+        other.un = __shfl_xor_sync(0xffffffffu, best.un, o);
+        other.it = __shfl_xor_sync(0xffffffffu, best.it, o);
+        best = cand_combine(best, other);
+      }
+      if (lane == 0) wbest[warp] = best;
+      __syncthreads();
+      best = wbest[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) best = cand_combine(best, wbest[w]);
+      min_val = best.v;
+      if (best.it < 0 || min_val == CUDART_INF) {  // infeasible (only with inf / nan costs); block-uniform
+        if (tid == 0) atomicOr(status, 2);
+        sink = -2;
+        break;
+      }
+      const int j = remaining[best.it];
+      const int r4c = row4col[j];
+      if (r4c == -1) sink = j; else i = r4c;
+      __syncthreads();   // everyone has read remaining[best.it] / wbest before they are overwritten
+      if (tid == 0) {
+        sc_list[n_sc] = static_cast<short>(j);
+        remaining[best.it] = remaining[num_remaining - 1];
+      }
+      ++n_sc;
+      --num_remaining;
+      __syncthreads();
+    }
+    if (sink < 0) break;
+    if (tid == 0) u[cur] += min_val;
+    for (int k = tid; k < n_sr; k += NT) {
+      const int r = sr_list[k];
+      if (r != cur) u[r] += min_val - spc[col4row[r]];
+    }
+    for (int k = tid; k < n_sc; k += NT) {
+      const int j = sc_list[k];
+      v[j] -= min_val - spc[j];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int j = sink;
+      for (;;) {
+        const int r = path[j];
+        row4col[j] = static_cast<short>(r);
+        const int t = col4row[r];
+        col4row[r] = static_cast<short>(j);
+        j = t;
+        if (r == cur) break;
+      }
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < Tmax; t += NT) match_pred[1LL * b * Tmax + t] = t < nr ? col4row[t] : -1;
+}
+
 // =====================================================================================================
 // K13 + K14: CTA per image.
 // =====================================================================================================
@@ -506,6 +614,22 @@ extern "C" int owl_lsap(const float* costT, const int* num_targets, int B, int P
   OWL_CHECK_ARG(B > 0 && P > 0 && Tmax > 0, "lsap: empty dimension");
   OWL_CHECK_ARG(Tmax <= P, "lsap: more targets (%d) than predictions (%d) is not supported", Tmax, P);
   OWL_CHECK_ARG(P < 32768, "lsap: P must fit int16");
+  if (B <= 2 * num_sms()) {
+    // few images: one CTA per image so that the slowest image finishes sooner
+    constexpr int NT = 256;
+    const size_t smem1 = lsap_smem_per_warp(P, Tmax);
+    OWL_CHECK_ARG(smem1 <= 227 * 1024, "lsap: P = %d needs %zu bytes of shared memory", P, smem1);
+    static size_t configured1 = 48 * 1024;
+    if (smem1 > configured1) {
+      OWL_CUDA(cudaFuncSetAttribute(lsap_block_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem1)));
+      configured1 = smem1;
+    }
+    lsap_block_kernel<NT><<<B, NT, smem1, static_cast<cudaStream_t>(stream)>>>(costT, num_targets, P, Tmax,
+                                                                               match_pred, status);
+    OWL_CUDA(cudaGetLastError());
+    return OWL_OK;
+  }
   const size_t smem = lsap_smem_per_warp(P, Tmax) * LSAP_WARPS;
   OWL_CHECK_ARG(smem <= 227 * 1024, "lsap: P = %d needs %zu bytes of shared memory", P, smem);
   static size_t configured = 0;

@@ -25,7 +25,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          act: str = "none", pre_out: Optional[torch.Tensor] = None, act_src: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None, rows_per_img: int = 0,
          out_mode: int = 0, argmax: Optional[torch.Tensor] = None, pool3: bool = False,
-         alpha_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+         alpha_dev: Optional[torch.Tensor] = None, cluster_m: int = 0) -> torch.Tensor:
     """D = alpha * A @ B^T with a fused epilogue; see `struct owl_gemm_args` in include/owl_b200.h."""
     assert a.dtype == torch.float16 and b.dtype == torch.float16 and a.is_cuda and b.is_cuda
     g = GemmArgs()
@@ -63,6 +63,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.out_mode = out_mode
     g.argmax = ptr(argmax)
     g.alpha_dev = ptr(alpha_dev)
+    g.cluster_m = cluster_m
     check(lib().owl_gemm(ctypes.byref(g), ctypes.c_void_p(stream_ptr())), "owl_gemm")
     return out
 

@@ -176,3 +176,33 @@ def test_full_size_qkv_timing():
     ms = e0.elapsed_time(e1) / 20
     print(f"\nqkv gemm {M}x{N}x{K}: {ms * 1e3:.1f} us, {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
     _check(out, a.double() @ b.double().T + bias.double(), 2e-3)
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("shape", [(300, 512, 136), (1154, 768, 768), (256, 256, 64), (9232, 768, 192)])
+def test_cluster_multicast_kk(bn, shape):
+    """2-CTA clusters (B tile TMA-multicast): odd numbers of M tiles, M/N/K tails, both epilogue families."""
+    ops = _ops()
+    M, N, K = shape
+    a, b = _rand((M, K), 21), _rand((N, K), 22, K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, M=M, N=N, K=K, bn=bn, bias=bias, resid=resid, cluster_m=2)
+    out16 = torch.zeros((M, N), device="cuda", dtype=torch.float16)
+    ops.gemm(a, b, out16, M=M, N=N, K=K, bn=bn, bias=bias, act="quick_gelu", cluster_m=2)
+    torch.cuda.synchronize()
+    z = a.double() @ b.double().T + bias.double()
+    _check(out, z + resid.double(), 1e-4)
+    _check(out16, z * torch.sigmoid(1.702 * z), 2e-3)
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_cluster_multicast_dgrad_b_mn(bn):
+    ops = _ops()
+    M, N, K = 1200, 520, 264          # dX[M,K] = dY[M,N] @ W[N,K], B = W read MN-major
+    dy, w = _rand((M, N), 23), _rand((N, K), 24)
+    out = torch.zeros((M, K), device="cuda")
+    ops.gemm(dy, w, out, M=M, N=K, K=N, b_mn=True, bn=bn, cluster_m=2)
+    torch.cuda.synchronize()
+    _check(out, dy.double() @ w.double(), 1e-4)

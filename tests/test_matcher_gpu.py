@@ -145,3 +145,16 @@ def test_degenerate_box_flag():
     ops.matcher_cost(sims.cuda(), pred.cuda(), lab.cuda(), tgt.cuda(), nt, costT, status)
     torch.cuda.synchronize()
     assert status.item() & 1
+
+
+def test_large_batch_uses_warp_per_image_solver():
+    """B > 2 x SM count takes the one-warp-per-image LSAP kernel (the matcher microbench path)."""
+    n, T = 640, 10
+    sims, pred, lab, tgt = synth.make_matcher_inputs(n, T, seed=21)
+    nt = torch.full((n,), T, dtype=torch.int32)
+    costT, match, out, _, _ = _run_device(sims, pred, lab, tgt, nt, None)
+    for b in (0, 1, 17, 333, 639):
+        rows, cols = mo.lsap(mo.cost_matrix(sims[b], pred[b], lab[b], tgt[b]).numpy())
+        exp = torch.full((T,), -1, dtype=torch.int32)
+        exp[torch.from_numpy(cols)] = torch.from_numpy(rows).int()
+        assert torch.equal(match[b], exp), b
