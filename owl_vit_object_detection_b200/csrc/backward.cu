@@ -37,6 +37,7 @@ __device__ __forceinline__ float4 f4_load_h(const __half* p) {
 // ------------------------------------------------------------------ gradient scale
 __global__ void amax_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
                             unsigned int* __restrict__ bits) {
+  pdl_grid_wait();
   float m = 0.f;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < na; i += 1LL * gridDim.x * blockDim.x)
     m = fmaxf(m, fabsf(a[i]));
@@ -48,6 +49,7 @@ __global__ void amax_kernel(const float* __restrict__ a, long long na, const flo
   if ((threadIdx.x & 31) == 0) atomicMax(bits, __float_as_uint(m));
 }
 __global__ void scale_from_amax_kernel(const unsigned int* __restrict__ bits, float target, float* __restrict__ gscale) {
+  pdl_grid_wait();
   const float amax = __uint_as_float(*bits);
   float s = 1.0f;
   if (amax > 0.f && isfinite(amax)) {
@@ -64,6 +66,7 @@ __global__ void scale_from_amax_kernel(const unsigned int* __restrict__ bits, fl
 // dfull[m, 3c + j] = S * dsims[m, c] if j == argmax[m, c] else 0   (reference src/models.py:36)
 __global__ void pool3_bwd_kernel(const float* __restrict__ dsims, const uint8_t* __restrict__ argmax,
                                  const float* __restrict__ gscale, __half* __restrict__ dfull, long long n) {
+  pdl_grid_wait();
   const float S = gscale[0];
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
     const float g = dsims[i] * S;
@@ -81,6 +84,7 @@ __global__ void pool3_bwd_kernel(const float* __restrict__ dsims, const uint8_t*
 template <typename OutT>
 __global__ void rownorm_bwd_kernel(const float* __restrict__ e, const float* __restrict__ dy, OutT* __restrict__ out,
                                    int rows, int E, int mode, const float* __restrict__ gscale) {
+  pdl_grid_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -132,6 +136,7 @@ __global__ void box_tail_bwd_kernel(const float* __restrict__ dboxes, const floa
                                     const float* __restrict__ w2, const __half* __restrict__ pre1,
                                     const float* __restrict__ gscale, float* __restrict__ dz,
                                     __half* __restrict__ dpre1, int M, int D) {
+  pdl_grid_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -163,6 +168,7 @@ __global__ void box_tail_bwd_kernel(const float* __restrict__ dboxes, const floa
 __global__ void box_w2_grad_kernel(const float* __restrict__ dz, const __half* __restrict__ h1,
                                    const float* __restrict__ gscale, float* __restrict__ dw2,
                                    float* __restrict__ db2, int M, int D) {
+  pdl_grid_wait();
   const int m0 = blockIdx.x * 64, m1 = min(M, m0 + 64);
   const float us = gscale[1];
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -189,6 +195,7 @@ __global__ void box_w2_grad_kernel(const float* __restrict__ dz, const __half* _
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long long ld, int M, int N, const float* __restrict__ gscale,
                               float* __restrict__ out) {
+  pdl_grid_wait();
   __shared__ float red[8][64];
   const int c = blockIdx.x * 64 + threadIdx.x * 2;
   const int m0 = blockIdx.y * 256;
@@ -225,6 +232,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, int M, int 
 // cancels most of dP's magnitude), dS fp16 [rows, ld]; n <= 1024 valid columns.
 __global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __restrict__ dp, __half* __restrict__ ds,
                                    long long rows, int n, int ld, float scale) {
+  pdl_grid_wait();
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -261,6 +269,7 @@ ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
               const float* __restrict__ gamma, const float* __restrict__ dx_add, float* __restrict__ dx,
               long long dx_stride, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D, float eps,
               int rows_per_cta, const float* __restrict__ gscale) {
+  pdl_grid_wait();
   extern __shared__ float lnb_sm[];  // [LNB_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D >> 7;
@@ -341,6 +350,7 @@ post_fuse_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ecls
                      float* __restrict__ dx, float* __restrict__ dcl, float* __restrict__ dg1, float* __restrict__ db1,
                      float* __restrict__ dg2, float* __restrict__ db2, int P, int D, float eps, int rows_per_cta,
                      const float* __restrict__ gscale) {
+  pdl_grid_wait();
   extern __shared__ float pf_sm[];  // [LNB_WARPS][5][D]: dg2, db2, dcl, dg1, db1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = D >> 7;
@@ -469,6 +479,7 @@ post_fuse_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ecls
 // state[0] = step count (as float), state[1] = 1 - beta1^step, state[2] = sqrt(1 - beta2^step): advanced on the
 // device so that a captured CUDA graph of the step replays with the right bias correction.
 __global__ void adamw_advance_kernel(float* __restrict__ state, float beta1, float beta2) {
+  pdl_grid_wait();
   const float step = state[0] + 1.0f;
   state[0] = step;
   state[1] = 1.0f - powf(beta1, step);
@@ -477,6 +488,7 @@ __global__ void adamw_advance_kernel(float* __restrict__ state, float beta1, flo
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, __half* __restrict__ p16, long long n, float lr, float beta1,
                              float beta2, float eps, float wd, const float* __restrict__ state, float grad_mul) {
+  pdl_grid_wait();
   const long long i = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const float bc1 = state[1], bc2_sqrt = state[2];
@@ -513,8 +525,8 @@ extern "C" int owl_grad_scale(const float* a, long long na, const float* b, long
   unsigned int* bits = reinterpret_cast<unsigned int*>(gscale + 2);
   OWL_CUDA(cudaMemsetAsync(bits, 0, sizeof(unsigned int), s));
   const int blocks = static_cast<int>(std::min<long long>((std::max(na, nb) + 255) / 256, 148LL * 8));
-  amax_kernel<<<blocks, 256, 0, s>>>(a, na, b, b ? nb : 0, bits);
-  scale_from_amax_kernel<<<1, 1, 0, s>>>(bits, target, gscale);
+  OWL_LAUNCH(amax_kernel, blocks, 256, 0, s, a, na, b, b ? nb : 0, bits);
+  OWL_LAUNCH(scale_from_amax_kernel, 1, 1, 0, s, bits, target, gscale);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -523,7 +535,7 @@ extern "C" int owl_pool3_bwd(const float* dsims, const uint8_t* argmax, const fl
                              long long n, void* stream) {
   OWL_CHECK_ARG(dsims && argmax && gscale && dfull_f16 && n > 0, "pool3_bwd: bad arguments");
   const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 16));
-  pool3_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dsims, argmax, gscale,
+  OWL_LAUNCH(pool3_bwd_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), dsims, argmax, gscale,
                                                                           static_cast<__half*>(dfull_f16), n);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -535,9 +547,9 @@ extern "C" int owl_rownorm_bwd(const float* e, const float* dy, void* out, int r
   OWL_CHECK_ARG(E % 128 == 0 && E <= 128 * BW_MAX_VEC, "rownorm_bwd: unsupported E = %d", E);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (query_mode)
-    rownorm_bwd_kernel<float><<<(rows + 7) / 8, 256, 0, s>>>(e, dy, static_cast<float*>(out), rows, E, 1, gscale);
+    OWL_LAUNCH(rownorm_bwd_kernel<float>, (rows + 7) / 8, 256, 0, s, e, dy, static_cast<float*>(out), rows, E, 1, gscale);
   else
-    rownorm_bwd_kernel<__half><<<(rows + 7) / 8, 256, 0, s>>>(e, dy, static_cast<__half*>(out), rows, E, 0, gscale);
+    OWL_LAUNCH(rownorm_bwd_kernel<__half>, (rows + 7) / 8, 256, 0, s, e, dy, static_cast<__half*>(out), rows, E, 0, gscale);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -549,9 +561,9 @@ extern "C" int owl_box_tail_bwd(const float* dboxes, const float* sig, const flo
                 "box_tail_bwd: bad arguments");
   OWL_CHECK_ARG(D % 4 == 0, "box_tail_bwd: D %% 4 != 0");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  box_tail_bwd_kernel<<<(M + 7) / 8, 256, 0, s>>>(dboxes, sig, w2, static_cast<const __half*>(pre1_f16), gscale, dz,
+  OWL_LAUNCH(box_tail_bwd_kernel, (M + 7) / 8, 256, 0, s, dboxes, sig, w2, static_cast<const __half*>(pre1_f16), gscale, dz,
                                                   static_cast<__half*>(dpre1_f16), M, D);
-  box_w2_grad_kernel<<<(M + 63) / 64, 256, 0, s>>>(dz, static_cast<const __half*>(h1_f16), gscale, dw2, db2, M, D);
+  OWL_LAUNCH(box_w2_grad_kernel, (M + 63) / 64, 256, 0, s, dz, static_cast<const __half*>(h1_f16), gscale, dw2, db2, M, D);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -561,8 +573,8 @@ extern "C" int owl_colsum(const void* x, int is_f16, long long ld, int M, int N,
   OWL_CHECK_ARG(x && out && M > 0 && N > 0 && N % 2 == 0 && ld % 2 == 0, "colsum: bad arguments (N, ld even)");
   dim3 grid((N + 63) / 64, (M + 255) / 256), block(32, 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (is_f16) colsum_kernel<__half><<<grid, block, 0, s>>>(static_cast<const __half*>(x), ld, M, N, gscale, out);
-  else colsum_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), ld, M, N, gscale, out);
+  if (is_f16) OWL_LAUNCH(colsum_kernel<__half>, grid, block, 0, s, static_cast<const __half*>(x), ld, M, N, gscale, out);
+  else OWL_LAUNCH(colsum_kernel<float>, grid, block, 0, s, static_cast<const float*>(x), ld, M, N, gscale, out);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -571,7 +583,7 @@ extern "C" int owl_softmax_bwd_f16(const void* probs, const float* dprobs, void*
                                    int ld, float scale, void* stream) {
   OWL_CHECK_ARG(probs && dprobs && dscores && rows > 0 && n > 0 && n <= 1024 && ld >= n,
                 "softmax_bwd: bad arguments (n <= 1024)");
-  softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(softmax_bwd_kernel, static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(probs), dprobs, static_cast<__half*>(dscores), rows, n, ld, scale);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -586,7 +598,7 @@ extern "C" int owl_layernorm_bwd(const float* x, long long x_stride, const float
   OWL_CHECK_ARG(!dx_add || dx, "layernorm_bwd: dx_add needs dx");
   const int rows_per_cta = rows >= 148 * 16 ? 32 : (rows >= 148 * 4 ? 8 : 4);
   const size_t smem = sizeof(float) * LNB_WARPS * 2 * D;
-  ln_bwd_kernel<<<(rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(ln_bwd_kernel, (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream), 
       x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma, dbeta, rows, D, eps, rows_per_cta, gscale);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -606,7 +618,7 @@ extern "C" int owl_post_fuse_bwd(const float* x, const float* ecls, const float*
     configured = smem;
   }
   dim3 grid((P + rows_per_cta - 1) / rows_per_cta, B);
-  post_fuse_bwd_kernel<<<grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(post_fuse_bwd_kernel, grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream), 
       x, ecls, g1, b1, g2, dfeats, dx, dcl, dg1, db1, dg2, db2, P, D, eps, rows_per_cta, gscale);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -618,8 +630,8 @@ extern "C" int owl_adamw(float* params, const float* grads, float* exp_avg, floa
   OWL_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && n > 0 && n % 4 == 0, "adamw: bad arguments");
   const long long threads = n / 4;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  adamw_advance_kernel<<<1, 1, 0, s>>>(state, beta1, beta2);
-  adamw_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(
+  OWL_LAUNCH(adamw_advance_kernel, 1, 1, 0, s, state, beta1, beta2);
+  OWL_LAUNCH(adamw_kernel, static_cast<unsigned>((threads + 255) / 256), 256, 0, s, 
       params, grads, exp_avg, exp_avg_sq, static_cast<__half*>(params_f16), n, lr, beta1, beta2, eps, weight_decay,
       state, grad_mul);
   OWL_CUDA(cudaGetLastError());

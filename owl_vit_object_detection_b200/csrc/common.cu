@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace owl {
@@ -64,6 +65,15 @@ int make_tensor_map_f16(CUtensorMap* out, const void* base, uint64_t inner, uint
     return OWL_ERR_DRIVER;
   }
   return OWL_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OWL_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

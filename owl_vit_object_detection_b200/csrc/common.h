@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 #include "../../include/owl_b200.h"
 
@@ -40,5 +41,51 @@ int make_tensor_map_f16(CUtensorMap* out, const void* base, uint64_t inner, uint
                         uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows);
 
 int num_sms();
+
+// Programmatic dependent launch (PDL): every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_grid_wait() (griddepcontrol.wait) before it
+// touches global memory, then releases its own dependents (griddepcontrol.launch_dependents).  The next kernel's
+// CTAs can therefore be scheduled onto SMs as the current kernel's CTAs retire and run their set-up (barrier init,
+// TMEM allocation, descriptor prefetch) under the current kernel's tail; a step is ~170 short kernels, so the
+// fill / drain bubbles are a measurable part of it.  OWL_PDL=0 in the environment turns the attribute off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define OWL_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  OWL_CUDA(::owl::launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, 1, __VA_ARGS__))
+
+#ifdef __CUDACC__
+// first statement of every kernel (after purely local set-up): wait for the producer grids, then let our own
+// dependents be scheduled as SMs free up
+__device__ __forceinline__ void pdl_grid_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 
 }  // namespace owl

@@ -35,6 +35,7 @@ __device__ __forceinline__ void store4(__half* p, float4 v) {
 template <int VEC>
 __global__ void im2col_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int IS, int ps,
                               int ld) {
+  pdl_grid_wait();
   const int g = IS / ps;
   const long long groups_per_row = IS / VEC;
   const long long total = 1LL * B * 3 * IS * groups_per_row;
@@ -74,6 +75,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long x_stride
                                  const float* __restrict__ beta, OutT* __restrict__ y, long long y_stride,
                                  int rows, int D, float eps, const float* __restrict__ cls_emb,
                                  const float* __restrict__ pos0, int tokens) {
+  pdl_grid_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -129,6 +131,7 @@ __global__ void post_fuse_kernel(const float* __restrict__ x, const float* __res
                                  const float* __restrict__ g1, const float* __restrict__ b1,
                                  const float* __restrict__ g2, const float* __restrict__ b2,
                                  __half* __restrict__ feats, int B, int P, int D, float eps) {
+  pdl_grid_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= B * P) return;
   const int lane = threadIdx.x & 31;
@@ -196,6 +199,7 @@ __global__ void post_fuse_kernel(const float* __restrict__ x, const float* __res
 // reference src/models.py:28-30  e / (||e|| + 1e-6)      (mode 0, image side)
 // reference src/models.py:31-33  q / ||q|| + 1e-6        (mode 1, query side; precedence quirk Q1)
 __global__ void rownorm_kernel(const float* __restrict__ e, __half* __restrict__ out, int rows, int E, int mode) {
+  pdl_grid_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -231,6 +235,7 @@ __global__ void rownorm_kernel(const float* __restrict__ e, __half* __restrict__
 __global__ void box_tail_kernel(const __half* __restrict__ h, const float* __restrict__ w,
                                 const float* __restrict__ bias, const float* __restrict__ box_bias,
                                 float* __restrict__ boxes, float* __restrict__ sig, int M, int P, int D) {
+  pdl_grid_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -272,6 +277,7 @@ __global__ void box_tail_kernel(const __half* __restrict__ h, const float* __res
 // ------------------------------------------------------------------ softmax over rows of fp16 scores (in place)
 // HF:398 softmax in fp32; rows of length n inside a [rows, ld] buffer; columns >= n are left untouched.
 __global__ void softmax_rows_kernel(__half* __restrict__ s, long long rows, int n, int ld) {
+  pdl_grid_wait();
   const long long row = blockIdx.x * 1LL * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -301,6 +307,7 @@ __global__ void softmax_rows_kernel(__half* __restrict__ s, long long rows, int 
 
 // ------------------------------------------------------------------ fp32 -> fp16 cast with scale
 __global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n, float scale) {
+  pdl_grid_wait();
   const long long i = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -324,8 +331,8 @@ extern "C" int owl_im2col_f16(const float* img, void* out, int B, int image_size
   const bool v8 = patch % 8 == 0 && ld % 8 == 0;
   const long long total = 1LL * B * 3 * image_size * (image_size / (v8 ? 8 : 2));
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
-  if (v8) im2col_kernel<8><<<blocks, 256, 0, s>>>(img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
-  else im2col_kernel<2><<<blocks, 256, 0, s>>>(img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
+  if (v8) OWL_LAUNCH(im2col_kernel<8>, blocks, 256, 0, s, img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
+  else OWL_LAUNCH(im2col_kernel<2>, blocks, 256, 0, s, img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -339,10 +346,10 @@ extern "C" int owl_layernorm(const float* x, long long x_stride, const float* ga
   OWL_CHECK_ARG(!cls_emb || (pos0 && tokens > 0), "layernorm: cls_emb needs pos0 and tokens");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (out_f16)
-    layernorm_kernel<__half><<<row_blocks(rows), ROW_WARPS * 32, 0, s>>>(x, x_stride, gamma, beta,
+    OWL_LAUNCH(layernorm_kernel<__half>, row_blocks(rows), ROW_WARPS * 32, 0, s, x, x_stride, gamma, beta,
         static_cast<__half*>(y), y_stride, rows, D, eps, cls_emb, pos0, tokens);
   else
-    layernorm_kernel<float><<<row_blocks(rows), ROW_WARPS * 32, 0, s>>>(x, x_stride, gamma, beta,
+    OWL_LAUNCH(layernorm_kernel<float>, row_blocks(rows), ROW_WARPS * 32, 0, s, x, x_stride, gamma, beta,
         static_cast<float*>(y), y_stride, rows, D, eps, cls_emb, pos0, tokens);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -352,7 +359,7 @@ extern "C" int owl_post_fuse(const float* x, const float* ecls, const float* g1,
                              const float* b2, void* feats, int B, int P, int D, float eps, void* stream) {
   OWL_CHECK_ARG(x && ecls && g1 && b1 && g2 && b2 && feats && B > 0 && P > 0, "post_fuse: null / empty argument");
   OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * MAX_VEC, "post_fuse: unsupported D = %d", D);
-  post_fuse_kernel<<<row_blocks(1LL * B * P), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(post_fuse_kernel, row_blocks(1LL * B * P), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), 
       x, ecls, g1, b1, g2, b2, static_cast<__half*>(feats), B, P, D, eps);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -361,7 +368,7 @@ extern "C" int owl_post_fuse(const float* x, const float* ecls, const float* g1,
 extern "C" int owl_rownorm_f16(const float* e, void* out, int rows, int E, int query_mode, void* stream) {
   OWL_CHECK_ARG(e && out && rows > 0, "rownorm: null / empty argument");
   OWL_CHECK_ARG(E % 128 == 0 && E <= 128 * MAX_VEC, "rownorm: unsupported E = %d", E);
-  rownorm_kernel<<<row_blocks(rows), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(rownorm_kernel, row_blocks(rows), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), 
       e, static_cast<__half*>(out), rows, E, query_mode);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -371,7 +378,7 @@ extern "C" int owl_box_tail(const void* h, const float* w, const float* bias, co
                             float* sig, int M, int P, int D, void* stream) {
   OWL_CHECK_ARG(h && w && bias && box_bias && boxes && sig && M > 0 && P > 0, "box_tail: null / empty argument");
   OWL_CHECK_ARG(D % 8 == 0, "box_tail: D %% 8 != 0");
-  box_tail_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(box_tail_kernel, row_blocks(M), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(h), w, bias, box_bias, boxes, sig, M, P, D);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -379,7 +386,7 @@ extern "C" int owl_box_tail(const void* h, const float* w, const float* bias, co
 
 extern "C" int owl_softmax_rows_f16(void* scores, long long rows, int n, int ld, void* stream) {
   OWL_CHECK_ARG(scores && rows > 0 && n > 0 && n <= 1024 && ld >= n, "softmax_rows: bad arguments (n <= 1024)");
-  softmax_rows_kernel<<<row_blocks(rows), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(softmax_rows_kernel, row_blocks(rows), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), 
       static_cast<__half*>(scores), rows, n, ld);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -390,7 +397,7 @@ extern "C" int owl_cast_f16(const float* src, void* dst, long long n, float scal
   OWL_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
                 "cast_f16: misaligned pointers");
   const long long threads = (n + 3) / 4;
-  cast_f16_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(cast_f16_kernel, static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), 
       src, static_cast<__half*>(dst), n, scale);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;

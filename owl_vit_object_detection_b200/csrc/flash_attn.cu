@@ -100,6 +100,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_wait();   // set-up above overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -325,7 +326,7 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, int B, int
     configured = true;
   }
   dim3 grid((S + FA_BM - 1) / FA_BM, H, B);
-  flash_attn_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, static_cast<cudaStream_t>(stream), 
       tmQ, tmKV, static_cast<__half*>(ctx_f16), S, D, scale * 1.4426950408889634f);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;

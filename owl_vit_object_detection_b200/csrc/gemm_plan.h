@@ -36,23 +36,7 @@ int gemm_launch_one(const GemmPlan& p, const typename Epi::Params& ep, cudaStrea
     OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN / CM)));
     configured = true;
   }
-  if constexpr (CM == 1) {
-    kern<<<p.grid, GEMM_THREADS, gemm_smem_bytes(BN / CM), s>>>(p.tmA, p.tmB, p.gs, ep);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p.grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = gemm_smem_bytes(BN / CM);
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CM;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    OWL_CUDA(cudaLaunchKernelEx(&cfg, kern, p.tmA, p.tmB, p.gs, ep));
-  }
+  OWL_CUDA(launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), gemm_smem_bytes(BN / CM), s, CM, p.tmA, p.tmB, p.gs, ep));
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

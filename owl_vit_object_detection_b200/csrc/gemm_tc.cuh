@@ -137,6 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (CM > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_wait();   // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (every CTA fills its own shared memory)

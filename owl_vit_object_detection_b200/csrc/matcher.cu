@@ -60,6 +60,7 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
                     const long long* __restrict__ labels, const float* __restrict__ tboxes,
                     const int* __restrict__ num_targets, float* __restrict__ costT, int P, int C, int Tmax,
                     int* __restrict__ status) {
+  pdl_grid_wait();
   extern __shared__ float sm[];
   float* prob = sm;                                   // [32][C + 1]
   float* pbox = prob + COST_ROWS * (C + 1);           // [32][4]
@@ -145,6 +146,7 @@ constexpr int LSAP_WARPS = 4;
 __global__ void __launch_bounds__(LSAP_WARPS * 32)
 lsap_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets, int B, int P, int Tmax,
             int* __restrict__ match_pred /*[B,Tmax]*/, int* __restrict__ status) {
+  pdl_grid_wait();
   extern __shared__ __align__(16) unsigned char lsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * LSAP_WARPS + warp;
@@ -251,6 +253,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 lsap_block_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets, int P, int Tmax,
                   int* __restrict__ match_pred /*[B,Tmax]*/, int* __restrict__ status) {
+  pdl_grid_wait();
   extern __shared__ __align__(16) unsigned char lsm[];
   constexpr int NW = NT / 32;
   __shared__ Cand wbest[NW];
@@ -418,6 +421,7 @@ match_loss_kernel(const float* __restrict__ sims, const float* __restrict__ boxe
                   long long* __restrict__ pred_sorted /*[B,Tmax]*/, long long* __restrict__ tgt_sorted /*[B,Tmax]*/,
                   float* __restrict__ losses /*[B,4]: ce,bg,bbox,giou*/, float* __restrict__ dsims /*[B,P,C]*/,
                   float* __restrict__ dl1 /*[B,Tmax,4]*/, float* __restrict__ dgiou /*[B,Tmax,4]*/, float inv_batch) {
+  pdl_grid_wait();
   extern __shared__ __align__(16) unsigned char smraw[];
   float* pbox = reinterpret_cast<float*>(smraw);          // [P][4]
   int* tc = reinterpret_cast<int*>(pbox + 4 * P);         // [P]
@@ -552,6 +556,7 @@ match_loss_kernel(const float* __restrict__ sims, const float* __restrict__ boxe
 
 // mean over images, fixed order (deterministic)
 __global__ void loss_reduce_kernel(const float* __restrict__ per_image, int B, float* __restrict__ out4) {
+  pdl_grid_wait();
   const int k = threadIdx.x;
   if (k < 4) {
     float s = 0.f;
@@ -566,6 +571,7 @@ __global__ void loss_backward_kernel(const float* __restrict__ dsims_unit, const
                                      const float* __restrict__ dgiou, const float* __restrict__ gup /*[4]*/,
                                      int B, int P, int C, int Tmax, int bg, float* __restrict__ dsims,
                                      float* __restrict__ dboxes) {
+  pdl_grid_wait();
   const float g_ce = gup[0], g_bg = gup[1], g_l1 = gup[2], g_gi = gup[3];
   const long long n = 1LL * B * P * C;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
@@ -596,7 +602,7 @@ extern "C" int owl_matcher_cost(const float* sims, const float* boxes, const lon
   const size_t smem = sizeof(float) * (COST_ROWS * (C + 1) + COST_ROWS * 4 + Tmax * 4) + sizeof(int) * Tmax;
   OWL_CHECK_ARG(smem <= 48 * 1024, "matcher_cost: C = %d / Tmax = %d need %zu bytes of shared memory", C, Tmax, smem);
   dim3 grid((P + COST_ROWS - 1) / COST_ROWS, B);
-  matcher_cost_kernel<<<grid, COST_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(matcher_cost_kernel, grid, COST_THREADS, smem, static_cast<cudaStream_t>(stream), 
       sims, boxes, labels, tboxes, num_targets, costT, P, C, Tmax, status);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -625,7 +631,7 @@ extern "C" int owl_lsap(const float* costT, const int* num_targets, int B, int P
                                     static_cast<int>(smem1)));
       configured1 = smem1;
     }
-    lsap_block_kernel<NT><<<B, NT, smem1, static_cast<cudaStream_t>(stream)>>>(costT, num_targets, P, Tmax,
+    OWL_LAUNCH(lsap_block_kernel<NT>, B, NT, smem1, static_cast<cudaStream_t>(stream), costT, num_targets, P, Tmax,
                                                                                match_pred, status);
     OWL_CUDA(cudaGetLastError());
     return OWL_OK;
@@ -637,7 +643,7 @@ extern "C" int owl_lsap(const float* costT, const int* num_targets, int B, int P
     OWL_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  lsap_kernel<<<(B + LSAP_WARPS - 1) / LSAP_WARPS, LSAP_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  OWL_LAUNCH(lsap_kernel, (B + LSAP_WARPS - 1) / LSAP_WARPS, LSAP_WARPS * 32, smem, static_cast<cudaStream_t>(stream), 
       costT, num_targets, B, P, Tmax, match_pred, status);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
@@ -660,11 +666,11 @@ extern "C" int owl_match_loss(const float* sims, const float* boxes, const long 
     OWL_CUDA(cudaFuncSetAttribute(match_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  match_loss_kernel<<<B, LOSS_THREADS, smem, s>>>(sims, boxes, labels, tboxes, num_targets, match_pred, scales, P, C,
+  OWL_LAUNCH(match_loss_kernel, B, LOSS_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, match_pred, scales, P, C,
                                                   Tmax, bg_label, tc_matched, tc_final, pred_sorted, tgt_sorted,
                                                   losses_per_image, dsims_unit, dl1, dgiou, 1.0f / B);
   OWL_CUDA(cudaGetLastError());
-  loss_reduce_kernel<<<1, 32, 0, s>>>(losses_per_image, B, losses_mean4);
+  OWL_LAUNCH(loss_reduce_kernel, 1, 32, 0, s, losses_per_image, B, losses_mean4);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -678,7 +684,7 @@ extern "C" int owl_loss_backward(const float* dsims_unit, const long long* tc_fi
   OWL_CUDA(cudaMemsetAsync(dboxes, 0, sizeof(float) * 4 * (size_t)B * P, s));
   const long long n = 1LL * B * P * C;
   const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 16));
-  loss_backward_kernel<<<blocks, 256, 0, s>>>(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, B, P, C, Tmax,
+  OWL_LAUNCH(loss_backward_kernel, blocks, 256, 0, s, dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, B, P, C, Tmax,
                                               bg_label, dsims, dboxes);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
