@@ -78,25 +78,69 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
     const int p = p0 + (i >> 2);
     pbox[i] = p < P ? boxes[(1LL * b * P + p) * 4 + (i & 3)] : 0.0f;
   }
-  // phase 1: softmax(sims[b, p, :])  (reference src/matcher.py:106-108)
-  for (int r = warp; r < COST_ROWS; r += COST_THREADS / 32) {
+  // phase 1: softmax(sims[b, p, :])  (reference src/matcher.py:106-108).  Eight lanes per row, four rows per warp,
+  // so the CTA's 32 rows are in flight at once: every lane issues all of its 128-bit loads before the first
+  // reduction (rows are 4 * C bytes apart, a warp access covers four rows).  Falls back to scalar loads when C is
+  // not a multiple of 4.
+  {
+    const int r = warp * 4 + (lane >> 3), sub = lane & 7;
     const int p = p0 + r;
-    if (p >= P) break;
-    const float* row = sims + (1LL * b * P + p) * C;
-    float m = -CUDART_INF_F;
-    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+    const bool row_ok = p < P;
+    const float* row = sims + (1LL * b * P + (row_ok ? p : 0)) * C;
+    constexpr int MAXV = 8;                       // up to 8 * 32 = 256 classes per row
+    const int nvec = (C + 31) / 32;               // float4 per lane
+    float4 v[MAXV];
+    const bool vec = (C & 3) == 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int k = 0; k < MAXV; ++k) {
+      if (k < nvec) {
+        const int c = k * 32 + sub * 4;
+        float4 t = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        if (row_ok && c < C) {
+          if (vec) {
+            t = __ldg(reinterpret_cast<const float4*>(row + c));
+          } else {
+            t.x = row[c];
+            if (c + 1 < C) t.y = row[c + 1];
+            if (c + 2 < C) t.z = row[c + 2];
+            if (c + 3 < C) t.w = row[c + 3];
+          }
+        }
+        v[k] = t;
+      }
+    }
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+      if (k < nvec) m = fmaxf(m, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float e = expf(fsub(row[c], m));
-      prob[r * (C + 1) + c] = e;
-      s += e;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      if (k < nvec) {
+        const int c = k * 32 + sub * 4;
+        v[k].x = c < C ? expf(fsub(v[k].x, m)) : 0.f;
+        v[k].y = c + 1 < C ? expf(fsub(v[k].y, m)) : 0.f;
+        v[k].z = c + 2 < C ? expf(fsub(v[k].z, m)) : 0.f;
+        v[k].w = c + 3 < C ? expf(fsub(v[k].w, m)) : 0.f;
+        s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float inv = fdiv(1.0f, s);
-    for (int c = lane; c < C; c += 32) prob[r * (C + 1) + c] = fmul(prob[r * (C + 1) + c], inv);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      if (k < nvec) {
+        const int c = k * 32 + sub * 4;
+        float* dst = prob + r * (C + 1) + c;
+        if (c < C) dst[0] = fmul(v[k].x, inv);
+        if (c + 1 < C) dst[1] = fmul(v[k].y, inv);
+        if (c + 2 < C) dst[2] = fmul(v[k].z, inv);
+        if (c + 3 < C) dst[3] = fmul(v[k].w, inv);
+      }
+    }
   }
   __syncthreads();
   // degenerate boxes: the reference asserts (src/matcher.py:34-35); we flag and let the host raise
@@ -599,6 +643,7 @@ extern "C" int owl_matcher_cost(const float* sims, const float* boxes, const lon
                                 void* stream) {
   OWL_CHECK_ARG(sims && boxes && labels && tboxes && num_targets && costT && status, "matcher_cost: null argument");
   OWL_CHECK_ARG(B > 0 && P > 0 && C > 0 && Tmax > 0, "matcher_cost: empty dimension");
+  OWL_CHECK_ARG(C <= 256, "matcher_cost: C = %d classes is more than the 256 this kernel keeps in registers", C);
   const size_t smem = sizeof(float) * (COST_ROWS * (C + 1) + COST_ROWS * 4 + Tmax * 4) + sizeof(int) * Tmax;
   OWL_CHECK_ARG(smem <= 48 * 1024, "matcher_cost: C = %d / Tmax = %d need %zu bytes of shared memory", C, Tmax, smem);
   dim3 grid((P + COST_ROWS - 1) / COST_ROWS, B);
