@@ -70,129 +70,123 @@ __global__ void im2col_kernel(const float* __restrict__ img, __half* __restrict_
 // y[r] = LN(x[r]) * gamma + beta.  Row r is read at x + r * x_stride (so a strided subset of rows, e.g.
 // the CLS rows, can be normalised).  If `cls_emb` is set, rows with r % tokens == 0 take their input
 // from cls_emb + pos[0] instead (the CLS row of the embedding, HF:338-343).
-template <typename OutT>
+// NV = D / 128 is a template parameter so that the row's loads are issued back to back with nothing between
+// them (the SM issues in order: a consumer or a branch between two loads exposes a full memory latency per load).
+template <typename OutT, int NV>
 __global__ void layernorm_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, OutT* __restrict__ y, long long y_stride,
-                                 int rows, int D, float eps, const float* __restrict__ cls_emb,
+                                 int rows, float eps, const float* __restrict__ cls_emb,
                                  const float* __restrict__ pos0, int tokens) {
-  pdl_grid_wait();
+  constexpr int D = NV * 128;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;
-  float4 v[MAX_VEC];
+  pdl_grid_wait();
+  if (row >= rows) return;
+  float4 v[NV], g[NV], be[NV];
   const bool is_cls = cls_emb != nullptr && (row % tokens) == 0;
   const float* xr = x + row * x_stride;
-  float s = 0.f;
+  if (!is_cls) {
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
-    if (i < nv) {
-      const int c = i * 128 + lane * 4;
-      if (is_cls) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(cls_emb + c));
-        const float4 p = __ldg(reinterpret_cast<const float4*>(pos0 + c));
-        v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
-      } else {
-        v[i] = *reinterpret_cast<const float4*>(xr + c);
-      }
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(cls_emb + i * 128 + lane * 4));
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pos0 + i * 128 + lane * 4));
+      v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
     }
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {   // in flight behind the row itself; first used after both reductions
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
+    be[i] = __ldg(reinterpret_cast<const float4*>(beta + i * 128 + lane * 4));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
-    if (i < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) / D + eps);
   OutT* yr = y + row * y_stride;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
-    if (i < nv) {
-      const int c = i * 128 + lane * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g.x + b.x;
-      o.y = (v[i].y - mean) * rstd * g.y + b.y;
-      o.z = (v[i].z - mean) * rstd * g.z + b.z;
-      o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      store4(yr + c, o);
-    }
+  for (int i = 0; i < NV; ++i) {
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g[i].x + be[i].x;
+    o.y = (v[i].y - mean) * rstd * g[i].y + be[i].y;
+    o.z = (v[i].z - mean) * rstd * g[i].z + be[i].z;
+    o.w = (v[i].w - mean) * rstd * g[i].w + be[i].w;
+    store4(yr + i * 128 + lane * 4, o);
   }
 }
 
 // ------------------------------------------------------------------ reference src/models.py:80-86 fused
 // feats[b,p] = LN2( LN1(x[b,1+p]) * ecls[b] )  with ecls[b] = LN1(x[b,0]) precomputed (fp32 [B,D]).
+template <int NV>
 __global__ void post_fuse_kernel(const float* __restrict__ x, const float* __restrict__ ecls,
                                  const float* __restrict__ g1, const float* __restrict__ b1,
                                  const float* __restrict__ g2, const float* __restrict__ b2,
-                                 __half* __restrict__ feats, int B, int P, int D, float eps) {
+                                 __half* __restrict__ feats, int B, int P, float eps) {
+  constexpr int D = NV * 128;
   pdl_grid_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= B * P) return;
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;
   const int b = row / P, p = row - b * P;
   const float* xr = x + (1LL * b * (P + 1) + 1 + p) * D;
   const float* cr = ecls + 1LL * b * D;
-  float4 v[MAX_VEC];
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nv) {
-      v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   float mean = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nv) {
-      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + bb * bb) + (c * c + d * d);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
   float rstd = rsqrtf(warp_sum(q) / D + eps);
   s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nv) {
-      const int c = i * 128 + lane * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(g1 + c));
-      const float4 be = __ldg(reinterpret_cast<const float4*>(b1 + c));
-      const float4 cl = __ldg(reinterpret_cast<const float4*>(cr + c));
-      v[i].x = ((v[i].x - mean) * rstd * g.x + be.x) * cl.x;
-      v[i].y = ((v[i].y - mean) * rstd * g.y + be.y) * cl.y;
-      v[i].z = ((v[i].z - mean) * rstd * g.z + be.z) * cl.z;
-      v[i].w = ((v[i].w - mean) * rstd * g.w + be.w) * cl.w;
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(g1 + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(b1 + c));
+    const float4 cl = __ldg(reinterpret_cast<const float4*>(cr + c));
+    v[i].x = ((v[i].x - mean) * rstd * g.x + be.x) * cl.x;
+    v[i].y = ((v[i].y - mean) * rstd * g.y + be.y) * cl.y;
+    v[i].z = ((v[i].z - mean) * rstd * g.z + be.z) * cl.z;
+    v[i].w = ((v[i].w - mean) * rstd * g.w + be.w) * cl.w;
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
   mean = warp_sum(s) / D;
   q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nv) {
-      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + bb * bb) + (c * c + d * d);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
   rstd = rsqrtf(warp_sum(q) / D + eps);
   __half* fr = feats + 1LL * row * D;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nv) {
-      const int c = i * 128 + lane * 4;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(g2 + c));
-      const float4 be = __ldg(reinterpret_cast<const float4*>(b2 + c));
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g.x + be.x;
-      o.y = (v[i].y - mean) * rstd * g.y + be.y;
-      o.z = (v[i].z - mean) * rstd * g.z + be.z;
-      o.w = (v[i].w - mean) * rstd * g.w + be.w;
-      store4(fr + c, o);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(g2 + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(b2 + c));
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + be.x;
+    o.y = (v[i].y - mean) * rstd * g.y + be.y;
+    o.z = (v[i].z - mean) * rstd * g.z + be.z;
+    o.w = (v[i].w - mean) * rstd * g.w + be.w;
+    store4(fr + c, o);
+  }
 }
 
 // ------------------------------------------------------------------ class head normalisations
@@ -345,12 +339,19 @@ extern "C" int owl_layernorm(const float* x, long long x_stride, const float* ga
                 128 * MAX_VEC);
   OWL_CHECK_ARG(!cls_emb || (pos0 && tokens > 0), "layernorm: cls_emb needs pos0 and tokens");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (out_f16)
-    OWL_LAUNCH(layernorm_kernel<__half>, row_blocks(rows), ROW_WARPS * 32, 0, s, x, x_stride, gamma, beta,
-        static_cast<__half*>(y), y_stride, rows, D, eps, cls_emb, pos0, tokens);
-  else
-    OWL_LAUNCH(layernorm_kernel<float>, row_blocks(rows), ROW_WARPS * 32, 0, s, x, x_stride, gamma, beta,
-        static_cast<float*>(y), y_stride, rows, D, eps, cls_emb, pos0, tokens);
+#define OWL_LN_CASE(NV)                                                                                          \
+  case NV:                                                                                                       \
+    if (out_f16)                                                                                                 \
+      OWL_LAUNCH((layernorm_kernel<__half, NV>), row_blocks(rows), ROW_WARPS * 32, 0, s, x, x_stride, gamma, beta, \
+                 static_cast<__half*>(y), y_stride, rows, eps, cls_emb, pos0, tokens);                          \
+    else                                                                                                         \
+      OWL_LAUNCH((layernorm_kernel<float, NV>), row_blocks(rows), ROW_WARPS * 32, 0, s, x, x_stride, gamma, beta, \
+                 static_cast<float*>(y), y_stride, rows, eps, cls_emb, pos0, tokens);                           \
+    break;
+  switch (D / 128) {
+    OWL_LN_CASE(1) OWL_LN_CASE(2) OWL_LN_CASE(3) OWL_LN_CASE(4) OWL_LN_CASE(5) OWL_LN_CASE(6) OWL_LN_CASE(7) OWL_LN_CASE(8)
+  }
+#undef OWL_LN_CASE
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -359,8 +360,15 @@ extern "C" int owl_post_fuse(const float* x, const float* ecls, const float* g1,
                              const float* b2, void* feats, int B, int P, int D, float eps, void* stream) {
   OWL_CHECK_ARG(x && ecls && g1 && b1 && g2 && b2 && feats && B > 0 && P > 0, "post_fuse: null / empty argument");
   OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * MAX_VEC, "post_fuse: unsupported D = %d", D);
-  OWL_LAUNCH(post_fuse_kernel, row_blocks(1LL * B * P), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), 
-      x, ecls, g1, b1, g2, b2, static_cast<__half*>(feats), B, P, D, eps);
+#define OWL_PF_CASE(NV)                                                                                         \
+  case NV:                                                                                                      \
+    OWL_LAUNCH(post_fuse_kernel<NV>, row_blocks(1LL * B * P), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), \
+               x, ecls, g1, b1, g2, b2, static_cast<__half*>(feats), B, P, eps);                                \
+    break;
+  switch (D / 128) {
+    OWL_PF_CASE(1) OWL_PF_CASE(2) OWL_PF_CASE(3) OWL_PF_CASE(4) OWL_PF_CASE(5) OWL_PF_CASE(6) OWL_PF_CASE(7) OWL_PF_CASE(8)
+  }
+#undef OWL_PF_CASE
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

@@ -8,8 +8,8 @@ static int pick_bn(int M, int N, int G, int split_k, int epilogue, bool b_mn) {
   const int mb = (M + GEMM_BM - 1) / GEMM_BM;
   int best = 0;
   double best_cost = 0;
-  const int cands[3] = {256, 128, 64};
-  for (int c = 0; c < 3; ++c) {
+  const int cands[4] = {256, 192, 128, 64};
+  for (int c = 0; c < 4; ++c) {
     const int bn = cands[c];
     if (bn > 64 && bn >= 2 * N && N > 0) continue;  // mostly padding
     const long long tiles = 1LL * mb * ((N + bn - 1) / bn) * G * split_k;
@@ -40,19 +40,20 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   p.epilogue = a.epilogue;
   const int G = a.batches_outer * a.heads;
   p.bn = bn ? bn : pick_bn(a.M, a.N, G, a.split_k, a.epilogue, p.b_mn);
-  OWL_CHECK_ARG(p.bn == 64 || p.bn == 128 || p.bn == 256, "gemm: N tile %d not supported", p.bn);
+  OWL_CHECK_ARG(p.bn == 64 || p.bn == 128 || p.bn == 192 || p.bn == 256, "gemm: N tile %d not supported", p.bn);
   // 2-CTA clusters (B tile multicast) for the big forward / dgrad GEMMs; args.cluster_m: 0 = auto, 1 = off, 2 = on
   {
     const int mb_ = (a.M + GEMM_BM - 1) / GEMM_BM;
     const bool eligible = !p.a_mn && p.bn >= 128 && a.epilogue != 2 && a.act != 2 && a.act != 4 && mb_ >= 2;
     const long long tiles_ = 1LL * mb_ * ((a.N + p.bn - 1) / p.bn) * G * a.split_k;
     if (a.cluster_m == 2) {
-      OWL_CHECK_ARG(eligible, "gemm: cluster_m = 2 is not built for this operand layout / epilogue / tile");
+      OWL_CHECK_ARG(eligible && !(p.bn == 192 && p.b_mn), "gemm: cluster_m = 2 is not built for this operand layout / epilogue / tile");
       p.cm = 2;
     } else if (a.cluster_m == 0) {
-      // measured on B200: the pair flavour wins on long-K problems (8192^3: 1.31 vs 1.22 PFLOP/s) and loses on the
-      // K <= 3072 layer shapes, whose time goes to the epilogue / L2 traffic rather than the MMA main loop
-      p.cm = (eligible && tiles_ >= 2 * num_sms() && a.K >= 6144) ? 2 : 1;
+      // measured on B200 (tools/sweep_gemm.py): the pair flavour wins when the main loop is long (fc2, K = 3072:
+      // 43.4 vs 47.4 us at bn = 192; 8192^3: 1.31 vs 1.22 PFLOP/s) and loses on the K = 768 layer shapes, whose
+      // time goes to the epilogue rather than the MMA main loop
+      p.cm = (eligible && tiles_ >= num_sms() && a.K >= 3072 && !(p.bn == 192 && p.b_mn)) ? 2 : 1;
     } else {
       OWL_CHECK_ARG(a.cluster_m == 1, "gemm: cluster_m must be 0, 1 or 2");
       p.cm = 1;

@@ -45,16 +45,22 @@ int gemm_launch_one(const GemmPlan& p, const typename Epi::Params& ep, cudaStrea
   switch (p.bn * 8 + p.cm) {                                                                  \
     case 64 * 8 + 1:  return gemm_launch_one<64, A_MN, B_MN, EPI>(p, params, s);              \
     case 128 * 8 + 1: return gemm_launch_one<128, A_MN, B_MN, EPI>(p, params, s);             \
+    case 192 * 8 + 1: return gemm_launch_one<192, A_MN, B_MN, EPI>(p, params, s);             \
     case 256 * 8 + 1: return gemm_launch_one<256, A_MN, B_MN, EPI>(p, params, s);             \
     default: set_error("gemm: unsupported N tile %d / cluster %d", p.bn, p.cm); return OWL_ERR_UNSUPPORTED; \
   }
 // forward / dgrad GEMMs additionally come in a 2-CTA-cluster flavour (B tile multicast)
+// the 192-wide pair flavour stages 96 B rows per CTA: K-major B only (MN-major B moves whole 64-wide chunks)
+#define OWL_GEMM_CASE_192_PAIR(A_MN, B_MN, EPI, params) \
+    case 192 * 8 + 2: if constexpr (!(B_MN)) return gemm_launch_one<192, A_MN, false, EPI, 2>(p, params, s); else break;
 #define OWL_GEMM_DISPATCH_BN_CM(A_MN, B_MN, EPI, params)                                      \
   switch (p.bn * 8 + p.cm) {                                                                  \
     case 64 * 8 + 1:  return gemm_launch_one<64, A_MN, B_MN, EPI>(p, params, s);              \
     case 128 * 8 + 1: return gemm_launch_one<128, A_MN, B_MN, EPI>(p, params, s);             \
+    case 192 * 8 + 1: return gemm_launch_one<192, A_MN, B_MN, EPI>(p, params, s);             \
     case 256 * 8 + 1: return gemm_launch_one<256, A_MN, B_MN, EPI>(p, params, s);             \
     case 128 * 8 + 2: return gemm_launch_one<128, A_MN, B_MN, EPI, 2>(p, params, s);          \
+    OWL_GEMM_CASE_192_PAIR(A_MN, B_MN, EPI, params)                                           \
     case 256 * 8 + 2: return gemm_launch_one<256, A_MN, B_MN, EPI, 2>(p, params, s);          \
     default: set_error("gemm: unsupported N tile %d / cluster %d", p.bn, p.cm); return OWL_ERR_UNSUPPORTED; \
   }

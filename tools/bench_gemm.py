@@ -38,6 +38,7 @@ if which in ("all", "qkv"):
     t(lambda: ops.gemm(x768, w_qkv, o2304, M=M, N=2304, K=768, bias=b2304, bn=bn, cluster_m=cm), "qkv  f16 bias", 2.0 * M * 2304 * 768)
 if which in ("all", "fc1"):
     t(lambda: ops.gemm(x768, w_1, o3072, M=M, N=3072, K=768, bias=b3072, act="quick_gelu", bn=bn, cluster_m=cm), "fc1  f16 bias qgelu", 2.0 * M * 3072 * 768)
+    t(lambda: ops.gemm(x768, w_1, o3072, M=M, N=3072, K=768, bias=b3072, bn=bn, cluster_m=cm), "fc1  f16 bias", 2.0 * M * 3072 * 768)
     t(lambda: ops.gemm(x768, w_1, o3072, M=M, N=3072, K=768, bn=bn, cluster_m=cm), "fc1  f16 plain", 2.0 * M * 3072 * 768)
 if which in ("all", "fc2"):
     t(lambda: ops.gemm(x3072, w_2, o32, M=M, N=768, K=3072, bias=b768, resid=res, bn=bn, cluster_m=cm), "fc2  f32 bias resid", 2.0 * M * 768 * 3072)

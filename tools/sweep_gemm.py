@@ -19,7 +19,7 @@ def t(fn):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 20 * 1e3
 print(f"M={M} N={N} K={K}   (us)")
-for bn in (128, 256):
+for bn in (128, 192, 256):
     for cm in (1, 2):
         r = [t(lambda: ops.gemm(a, b, o16, M=M, N=N, K=K, bn=bn, cluster_m=cm)),
              t(lambda: ops.gemm(a, b, o16, M=M, N=N, K=K, bn=bn, cluster_m=cm, bias=bias, act="quick_gelu")),
