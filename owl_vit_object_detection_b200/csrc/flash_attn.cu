@@ -1,19 +1,26 @@
 // Fused attention forward for the ViT encoder (HF:379-404: softmax(q k^T / sqrt(dh)) v, no mask, no dropout)
 // on tcgen05 tensor cores: scores never leave the SM.
 //
-//   CTA            = one (image, head, 128-query tile); 320 threads
-//   warp 0         = TMA producer: Q tile once, then K/V blocks of 208 keys through a 3-stage ring
-//   warp 1         = MMA issuer:   S_j = Q K_j^T  (128 x 208 x 64, operands in swizzled smem, fp32 in TMEM)
-//                                  O  += P_j V_j  (128 x 64 x 208, A = P_j read straight from TMEM, B = V_j smem)
-//   warps 2..9     = softmax: two threads per query row (TMEM lane = row; warps 2..5 take key columns 0..111 of a
-//                    block, warps 6..9 columns 112..207, so every SM sub-partition interleaves two softmax warps):
-//                    running max / sum in fp32 (row max exchanged through shared memory), exp2 on the MUFU, P_j
-//                    written back over S_j in TMEM as packed fp16, O rescaled in TMEM when the max grows; final
-//                    O / l written to ctx as fp16
-//   TMEM (512 col) = S/P buffer 0 @0, S/P buffer 1 @224, O @448 (64 columns)
+//   CTA            = one (image, head, 128-query tile); 288 threads (112 registers each); TWO CTAs per SM
+//   warp 0         = control (one elected lane): TMA producer (Q tile once, K/V blocks of 128 keys through a
+//                    2-stage ring) and MMA issuer:
+//                                  S_j = Q K_j^T  (128 x 128 x 64, operands in swizzled smem, fp32 in TMEM)
+//                                  O  += P_j V_j  (128 x 64 x 128, A = P_j read straight from TMEM, B = V_j smem)
+//   warps 1..8     = softmax: two threads per query row (TMEM lane = row; warps 1..4 take key columns 0..63 of a
+//                    block, warps 5..8 columns 64..127, so every SM sub-partition interleaves two softmax warps)
+//   TMEM (256 col) = S @0 (128 fp32 columns), O @128 (64), P @192 (128 keys as packed fp16 = 64 columns)
 //
-// 577 tokens = 4.5 query tiles and 2.77 key blocks: out-of-range rows are zero-filled by TMA (per-image bounds in
-// the tensor map), out-of-range key columns are masked to -inf before the softmax.
+// What bounds this kernel at head_dim 64 is not the tensor pipe: per 128 x 128 block the two MMAs take ~512 clk,
+// while reading S out of TMEM once (64 KB at 64 B/clk/SM) and the 16384 exp2 on the 16-lane MUFU take ~1024 clk
+// each.  So S is read ONCE per block: every block after the first is exponentiated optimistically against the
+// running maximum while its own maximum is tracked on the side; only if some row's maximum grew by more than 2^8
+// (exponent domain) is the block redone against the new maximum and O rescaled (S is still intact because P has
+// its own TMEM columns).  Probabilities therefore stay <= 256 (fp16-exact range), sums are fp32, and the final
+// O / l removes the common factor.
+//
+// 577 tokens = 4.5 query tiles and 4.5 key blocks: out-of-range rows are zero-filled by TMA (per-image bounds in
+// the tensor map), out-of-range key columns are masked to -inf; the last block only computes the 16-key chunks
+// that hold a key.
 #include "common.h"
 #include "ptx.cuh"
 #include <stdlib.h>
@@ -22,33 +29,22 @@ namespace owl {
 
 constexpr int FA_BM = 128;       // queries per CTA
 constexpr int FA_DH = 64;        // head dim
-constexpr int FA_THREADS = 320;
+constexpr int FA_THREADS = 288;   // control warp + 8 softmax warps
 constexpr int FA_Q_BYTES = FA_BM * FA_DH * 2;       // 16 KB
 
-// Two tilings of the same kernel:
-//   Wide   : 208 keys per block (3 blocks = 624 >= 577 tokens), two S buffers so that S_{j+1} is computed while the
-//            softmax of block j runs, 3-stage K/V ring, all 512 TMEM columns, one CTA per SM.
-//   Narrow : 128 keys per block (5 blocks), one S buffer, 2-stage ring, 256 TMEM columns and ~84 KB of shared
-//            memory, so that TWO CTAs share an SM: their TMA / MMA / softmax phases interleave, which hides the
-//            per-tile start-up and tail that the serial chain of a single CTA leaves exposed (measured timeline:
-//            1.5 us start-up + 3 x 2.4 us softmax + 1.6 us tail per tile in the Wide tiling).
-template <int BN_, int NSBUF_, int STAGES_, int SPLIT_, int MINCTAS_>
+template <int BN_, int STAGES_, int MINCTAS_>
 struct FaCfg {
   static constexpr int BN = BN_;           // keys per block (UMMA N, multiple of 16)
-  static constexpr int NSBUF = NSBUF_;     // S/P buffers in TMEM
   static constexpr int STAGES = STAGES_;   // K/V ring depth
-  static constexpr int SPLIT = SPLIT_;     // key columns [0, SPLIT) -> softmax half 0, [SPLIT, BN) -> half 1
+  static constexpr int SPLIT = BN_ / 2;    // key columns [0, SPLIT) -> softmax half 0, [SPLIT, BN) -> half 1
   static constexpr int MINCTAS = MINCTAS_;
   static constexpr int KV_BYTES = BN * FA_DH * 2;   // multiple of 1024: every block stays swizzle-aligned
   static constexpr int SMEM = FA_Q_BYTES + 2 * STAGES * KV_BYTES + 1024 + 256 + 2 * 2 * 128 * 4;
-  static constexpr uint32_t TMEM_COLS = NSBUF == 2 ? 512 : 256;
-  static constexpr uint32_t TMEM_S0 = 0, TMEM_S1 = 224, TMEM_O = NSBUF == 2 ? 448 : 128;
-  static_assert(BN % 16 == 0 && SPLIT % 16 == 0 && KV_BYTES % 1024 == 0, "tile shape");
-  // TMEM column (relative to the S buffer) where the packed fp16 probabilities of key chunk c live
-  static __host__ __device__ constexpr int p_col(int c) { return c < SPLIT / 16 ? 8 * c : SPLIT + 8 * (c - SPLIT / 16); }
+  static constexpr uint32_t TMEM_COLS = 256;
+  static constexpr uint32_t TMEM_S = 0, TMEM_O = BN, TMEM_P = BN + FA_DH;
+  static_assert(BN == 128 && TMEM_P + BN / 2 <= TMEM_COLS && KV_BYTES % 1024 == 0, "tile shape");
 };
-using FaWide = FaCfg<208, 2, 3, 112, 1>;
-using FaNarrow = FaCfg<128, 1, 2, 64, 2>;
+using FaNarrow = FaCfg<128, 2, 2>;
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -101,8 +97,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   };
   constexpr int FA_BN = Cfg::BN, FA_STAGES = Cfg::STAGES, FA_KV_BYTES = Cfg::KV_BYTES, FA_SPLIT = Cfg::SPLIT;
-  constexpr int NSBUF = Cfg::NSBUF;
-  constexpr uint32_t FA_TMEM_S0 = Cfg::TMEM_S0, FA_TMEM_S1 = Cfg::TMEM_S1, FA_TMEM_O = Cfg::TMEM_O;
+  constexpr uint32_t FA_TMEM_S = Cfg::TMEM_S, FA_TMEM_O = Cfg::TMEM_O, FA_TMEM_P = Cfg::TMEM_P;
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -110,8 +105,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* sV = sK + FA_STAGES * FA_KV_BYTES;
   uint64_t* kv_full = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_KV_BYTES);
   uint64_t* kv_empty = kv_full + FA_STAGES;
-  uint64_t* s_full = kv_empty + FA_STAGES;   // [2]
-  uint64_t* p_full = s_full + 2;             // [2]
+  uint64_t* s_full = kv_empty + FA_STAGES;   // [1] (slot [1] unused)
+  uint64_t* p_full = s_full + 2;             // [1]
   uint64_t* o_full = p_full + 2;             // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   float* xch = reinterpret_cast<float*>(kv_full) + 64;   // [2 block parities][2 halves][128] row max (and final row sum) exchange
@@ -124,11 +119,13 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 0) {
+    __syncwarp();
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -139,158 +136,188 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (threadIdx.x == 64) stamp(0);
   pdl_grid_wait();   // set-up above overlaps the previous kernel's tail
   if (threadIdx.x == 64) stamp(1);
+  if (dbg != nullptr && threadIdx.x == 64) {
+    const long long cta = blockIdx.x + gridDim.x * (blockIdx.y + 1LL * gridDim.y * blockIdx.z);
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[64 + 3 * cta] = t;
+  }
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j % FA_STAGES;
-        const uint32_t ph = (j / FA_STAGES) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * FA_KV_BYTES + (j == 0 ? FA_Q_BYTES : 0));
-        if (j == 0) tma_load_3d(sQ, &tmQ, &kv_full[st], h * FA_DH, q0, b);
-        tma_load_3d(sK + st * FA_KV_BYTES, &tmKV, &kv_full[st], D + h * FA_DH, j * FA_BN, b);
-        tma_load_3d(sV + st * FA_KV_BYTES, &tmKV, &kv_full[st], 2 * D + h * FA_DH, j * FA_BN, b);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
+    // ------------------------------------------------ control warp: TMA producer + MMA issuer (one elected lane).
+    // One warp for both roles keeps the CTA at 9 warps, i.e. 112 registers per thread with two CTAs per SM, which
+    // is what lets a softmax thread hold its 64 scores of a block in registers.
     constexpr uint32_t IDESC_S = make_idesc_f16(FA_BM, FA_BN, false, false);
     constexpr uint32_t IDESC_O = make_idesc_f16(FA_BM, FA_DH, false, true);
     const uint32_t aQ = smem_u32(sQ);
-    auto issue_s = [&](int j) {
+    auto load_kv = [&](int j) {   // K/V block j -> ring slot j % STAGES (+ the Q tile with block 0)
+      const int st = j % FA_STAGES;
+      mbar_arrive_expect_tx(&kv_full[st], 2 * FA_KV_BYTES + (j == 0 ? FA_Q_BYTES : 0));
+      if (j == 0) tma_load_3d(sQ, &tmQ, &kv_full[st], h * FA_DH, q0, b);
+      tma_load_3d(sK + st * FA_KV_BYTES, &tmKV, &kv_full[st], D + h * FA_DH, j * FA_BN, b);
+      tma_load_3d(sV + st * FA_KV_BYTES, &tmKV, &kv_full[st], 2 * D + h * FA_DH, j * FA_BN, b);
+    };
+    auto issue_s = [&](int j) {   // S_j = Q K_j^T
       const int st = j % FA_STAGES;
       mbar_wait(&kv_full[st], (j / FA_STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t d = tmem_base + ((j % NSBUF) ? FA_TMEM_S1 : FA_TMEM_S0);
-        const uint32_t bK = smem_u32(sK + st * FA_KV_BYTES);
+      const uint32_t bK = smem_u32(sK + st * FA_KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < FA_DH / 16; ++k)
-          umma_f16(d, make_sdesc_sw128(aQ + k * 32, 0, 1024), make_sdesc_sw128(bK + k * 32, 0, 1024), IDESC_S,
-                   k > 0 ? 1u : 0u);
-        umma_commit(&s_full[j % NSBUF]);
-      }
-      __syncwarp();
+      for (int k = 0; k < FA_DH / 16; ++k)
+        umma_f16(tmem_base + FA_TMEM_S, make_sdesc_sw128(aQ + k * 32, 0, 1024), make_sdesc_sw128(bK + k * 32, 0, 1024),
+                 IDESC_S, k > 0 ? 1u : 0u);
+      umma_commit(s_full);
     };
-    if (NSBUF == 2) issue_s(0);
-    for (int j = 0; j < n_blocks; ++j) {
-      // two buffers: S_{j+1} runs ahead of the softmax of block j; one buffer: S_j follows P.V_{j-1} in issue order
-      if (NSBUF == 2) { if (j + 1 < n_blocks) issue_s(j + 1); } else { issue_s(j); }
-      mbar_wait(&p_full[j % NSBUF], (j / NSBUF) & 1);
-      tc_fence_after();
-      if (lane == 0) {
+    if (lane == 0) {
+      for (int j = 0; j < FA_STAGES && j < n_blocks; ++j) load_kv(j);
+      issue_s(0);
+      for (int j = 0; j < n_blocks; ++j) {
         const int st = j % FA_STAGES;
-        const uint32_t aP = tmem_base + ((j % NSBUF) ? FA_TMEM_S1 : FA_TMEM_S0);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
         const uint32_t bV = smem_u32(sV + st * FA_KV_BYTES);
+        // chunks of 16 keys; the last block of an image stops at the chunk that still holds a key
+        const int nk = (min(FA_BN, S - j * FA_BN) + 15) / 16;
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k)
-          umma_f16_ts(tmem_base + FA_TMEM_O, aP + Cfg::p_col(k), make_sdesc_sw128(bV + k * 2048, 8192, 1024), IDESC_O,
-                      (j > 0 || k > 0) ? 1u : 0u);
+          if (k < nk)
+            umma_f16_ts(tmem_base + FA_TMEM_O, tmem_base + FA_TMEM_P + 8 * k, make_sdesc_sw128(bV + k * 2048, 8192, 1024),
+                        IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
+        // S_{j+1} follows P V_j in issue order; nothing reads S_j any more (the softmax threads arrived on p_full)
+        if (j + 1 < n_blocks) issue_s(j + 1);
+        // refill the slot P V_j is draining; the load has the whole softmax of block j + 1 to land
+        if (j + FA_STAGES < n_blocks) {
+          mbar_wait(&kv_empty[st], (j / FA_STAGES) & 1);
+          load_kv(j + FA_STAGES);
+        }
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------ softmax / correction / epilogue: two threads per query row
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;                 // 0: key columns [0, 112), 1: [112, 208) of every block
+    const int quad = warp & 3;                        // TMEM lane quadrant a warp may touch = warp id % 4
+    const int half = (warp - 1) >> 2;                 // 0: key columns [0, 64), 1: [64, 128) of every block
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    constexpr int C0 = FA_SPLIT / 16, C1 = FA_BN / 16; // chunk ranges: half 0 = [0, C0), half 1 = [C0, C1)
-    const int cb = half ? C0 : 0, ce = half ? C1 : C0;
+    static_assert(FA_SPLIT == 64, "softmax code below: 64 key columns per thread, two groups of 32");
     auto sync_softmax = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    constexpr float kLazy = 8.0f;
+    const uint32_t sbuf = tmem_base + lane_addr + FA_TMEM_S + half * FA_SPLIT;
+    const uint32_t pbuf = tmem_base + lane_addr + FA_TMEM_P + half * (FA_SPLIT / 2);
     float m_run = -INFINITY, l_run = 0.f;
+
     for (int j = 0; j < n_blocks; ++j) {
-      const uint32_t sbuf = tmem_base + lane_addr + ((j % NSBUF) ? FA_TMEM_S1 : FA_TMEM_S0);
-      const int valid = min(FA_BN, S - j * FA_BN);   // key columns of this block that exist
-      const bool full = valid == FA_BN;               // only the last block of an image is partial
-      mbar_wait(&s_full[j % NSBUF], (j / NSBUF) & 1);
+      const int valid = min(FA_BN, S - j * FA_BN);    // key columns of this block that exist
+      const int my_valid = valid - half * FA_SPLIT;   // ... among this thread's 64 (<= 0: none)
+      float* xj = xch + (j & 1) * 256;   // double-buffered: block j + 1 must not overwrite what a slow partner still reads
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (threadIdx.x == 64 && j < 6) stamp(2 + 4 * j);
-      // pass A: maximum over this thread's columns, then over the row
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll 1
-      for (int c0 = cb; c0 < ce; c0 += 2) {
-        if (c0 * 16 >= valid) break;
-        uint32_t r[32];
-        const int nchunk = min(2, ce - c0);
+      if (j == 0) {
+        // first block: the maximum has to be known before anything can be exponentiated
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-          if (q < nchunk) tmem_ld16(sbuf + (c0 + q) * 16, r + q * 16);
-        tmem_ld_wait();
+        for (int g = 0; g < 2; ++g) {
+          if (g * 32 < my_valid) {
+            uint32_t r[32];
+            tmem_ld32(sbuf + g * 32, r);
+            tmem_ld_wait();
+            if (my_valid >= g * 32 + 32) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          if (i < nchunk * 16) {
-            float a = __uint_as_float(r[i]), b2 = __uint_as_float(r[i + 1]);
-            if (!full) {
-              a = (c0 * 16 + i < valid) ? a : -INFINITY;
-              b2 = (c0 * 16 + i + 1 < valid) ? b2 : -INFINITY;
+              for (int i = 0; i < 32; i += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(r[i]));     mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (g * 32 + i < my_valid) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
             }
-            mx0 = fmaxf(mx0, a);
-            mx1 = fmaxf(mx1, b2);
           }
         }
+        xj[half * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        sync_softmax();
+        m_run = fmaxf(xj[row], xj[128 + row]);        // finite: key 0 always exists
+        if (threadIdx.x == 64) stamp(3);
       }
-      float* xj = xch + (j & 1) * 256;   // double-buffered: block j + 1 must not overwrite what a slow partner still reads
-      xj[half * 128 + row] = fmaxf(mx0, mx1);
-      sync_softmax();
-      const float m_new = fmaxf(m_run, fmaxf(xj[row], xj[128 + row]));
-      const float mc = m_new * scale_log2;
-      if (threadIdx.x == 64 && j < 6) stamp(3 + 4 * j);
-      // pass B: p = exp2(s * c - m * c) as packed fp16, written IN PLACE over the columns this thread has already
-      // consumed: key chunk c (16 fp32 columns at 16c) becomes 8 packed columns at fa_p_col(c), which always trails
-      // the thread's own read position and never leaves its half.  The P.V MMAs address each chunk individually, so
-      // P does not have to be contiguous.
-      float sum0 = 0.f, sum1 = 0.f;
+      // Blocks after the first: optimistic single pass against the running maximum; the block's own maximum is
+      // checked afterwards and, rarely, the pass is repeated against the new maximum (attempt 1).
+      float m_new = m_run, sum = 0.f;
+      bool regrown = false;
 #pragma unroll 1
-      for (int c = cb; c < ce; ++c) {
-        uint32_t r[16], pk[8];
-        tmem_ld16(sbuf + c * 16, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -mc));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -mc));
-          if (!full) {
-            p0 = (c * 16 + 2 * i < valid) ? p0 : 0.f;
-            p1 = (c * 16 + 2 * i + 1 < valid) ? p1 : 0.f;
-          }
-          sum0 += p0;
-          sum1 += p1;
-          const __half2 hp = __floats2half2_rn(p0, p1);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        // one pass over this thread's (up to) 64 scores, 16 at a time with the next chunk's TMEM load in flight
+        // behind the current chunk's arithmetic: P = exp2(s * c - mc) as packed fp16 (key chunk of 16 -> 8 columns)
+        const float mc = m_new * scale_log2;
+        float sum0 = 0.f, sum1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+        uint32_t ra[16], rb[16];
+        if (my_valid > 0) {
+          tmem_ld16(sbuf, ra);
+          tmem_ld_wait();
         }
-        tmem_st8(sbuf + Cfg::p_col(c), pk);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 16 < my_valid) {       // warp-uniform; chunks without keys are skipped by the P.V MMAs as well
+            uint32_t* rc = (c & 1) ? rb : ra;
+            uint32_t* rn = (c & 1) ? ra : rb;
+            if (c + 1 < 4 && (c + 1) * 16 < my_valid) tmem_ld16(sbuf + (c + 1) * 16, rn);
+            if (my_valid < c * 16 + 16) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c * 16 + i >= my_valid) rc[i] = 0xff800000u;   // -inf -> p = 0
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float s0 = __uint_as_float(rc[2 * i]), s1 = __uint_as_float(rc[2 * i + 1]);
+              mx0 = fmaxf(mx0, s0);
+              mx1 = fmaxf(mx1, s1);
+              const float p0 = fast_exp2(fmaf(s0, scale_log2, -mc));
+              const float p1 = fast_exp2(fmaf(s1, scale_log2, -mc));
+              sum0 += p0;
+              sum1 += p1;
+              const __half2 hp = __floats2half2_rn(p0, p1);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
+            }
+            tmem_st8(pbuf + c * 8, pk);
+            tmem_ld_wait();              // chunk c + 1 has landed behind the arithmetic above
+          }
+        }
+        sum = sum0 + sum1;
+        if (j == 0 || attempt == 1) break;
+        xj[half * 128 + row] = fmaxf(mx0, mx1);
+        sync_softmax();
+        const float m_blk = fmaxf(xj[row], xj[128 + row]);
+        const bool grow = (m_blk - m_run) * scale_log2 > kLazy;   // same verdict in both threads of a row
+        if (threadIdx.x == 64 && j < 6) stamp(3 + 4 * j);
+        if (!__any_sync(0xffffffffu, grow)) break;
+        // rows that did not grow reproduce the same values in the second attempt
+        m_new = grow ? m_blk : m_run;
+        regrown = true;
+        tmem_st_wait();
       }
-      const float sum = sum0 + sum1;
-      if (threadIdx.x == 64 && j < 6) stamp(4 + 4 * j);
-      if (j > 0) {
+      if (regrown) {
         // O was accumulated against the old maximum: rescale it once P V_{j-1} has retired (32 columns per half)
-        const float alpha = fast_exp2((m_run - m_new) * scale_log2);
+        const float alpha = fast_exp2((m_run - m_new) * scale_log2);   // 1 for rows that did not grow
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          const uint32_t obuf = tmem_base + lane_addr + FA_TMEM_O + half * 32;
+        const uint32_t obuf = tmem_base + lane_addr + FA_TMEM_O + half * 32;
+        uint32_t o[32];
+        tmem_ld32(obuf, o);
+        tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[16];
-            tmem_ld16(obuf + c * 16, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st16(obuf + c * 16, r);
-          }
-        }
-        l_run = l_run * alpha + sum;
-      } else {
-        l_run = sum;
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(obuf, o);
+        l_run *= alpha;
+        m_run = m_new;
       }
-      m_run = m_new;
+      l_run += sum;
+      if (threadIdx.x == 64 && j < 6) stamp(4 + 4 * j);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[j % NSBUF]);
+      mbar_arrive(p_full);
       if (threadIdx.x == 64 && j < 6) stamp(5 + 4 * j);
     }
     // epilogue: ctx[b, q0 + row, h * 64 + half * 32 ..] = O / l   (l = sum of both halves' partial sums)
@@ -327,9 +354,18 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 
   if (threadIdx.x == 64) stamp(31);
+  if (dbg != nullptr && threadIdx.x == 64) {   // development only: per-CTA [start, end, sm] after the 64 phase stamps
+    const long long cta = blockIdx.x + gridDim.x * (blockIdx.y + 1LL * gridDim.y * blockIdx.z);
+    long long t;
+    uint32_t sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    dbg[64 + 3 * cta + 1] = t;
+    dbg[64 + 3 * cta + 2] = sm;
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -353,27 +389,19 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, int B, int
   OWL_CHECK_ARG(qkv_f16 && ctx_f16 && B > 0 && S > 0 && H > 0, "flash_attn_fwd: bad arguments");
   OWL_CHECK_ARG(head_dim == FA_DH, "flash_attn_fwd: head_dim %d is not built (only 64)", head_dim);
   const int D = H * head_dim;
-  // tiling: Narrow (two CTAs per SM) unless OWL_FA_WIDE=1
-  static int wide = -1;
-  if (wide < 0) { const char* e = getenv("OWL_FA_WIDE"); wide = (e && e[0] == '1') ? 1 : 0; }
   CUtensorMap tmQ, tmKV;
   int rc = make_qkv_map(&tmQ, qkv_f16, B, S, D, FA_BM);
   if (rc) return rc;
-  rc = make_qkv_map(&tmKV, qkv_f16, B, S, D, wide ? FaWide::BN : FaNarrow::BN);
+  rc = make_qkv_map(&tmKV, qkv_f16, B, S, D, FaNarrow::BN);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    OWL_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel<FaWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaWide::SMEM));
     OWL_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel<FaNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, FaNarrow::SMEM));
     configured = true;
   }
   dim3 grid((S + FA_BM - 1) / FA_BM, H, B);
   const float sl2 = scale * 1.4426950408889634f;
-  if (wide)
-    OWL_LAUNCH(flash_attn_fwd_kernel<FaWide>, grid, FA_THREADS, FaWide::SMEM, static_cast<cudaStream_t>(stream), tmQ, tmKV,
-               static_cast<__half*>(ctx_f16), S, D, sl2, g_fa_dbg);
-  else
-    OWL_LAUNCH(flash_attn_fwd_kernel<FaNarrow>, grid, FA_THREADS, FaNarrow::SMEM, static_cast<cudaStream_t>(stream), tmQ,
+  OWL_LAUNCH(flash_attn_fwd_kernel<FaNarrow>, grid, FA_THREADS, FaNarrow::SMEM, static_cast<cudaStream_t>(stream), tmQ,
                tmKV, static_cast<__half*>(ctx_f16), S, D, sl2, g_fa_dbg);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
