@@ -1,29 +1,28 @@
 // Fused attention forward for the ViT encoder (HF:379-404: softmax(q k^T / sqrt(dh)) v, no mask, no dropout)
 // on tcgen05 tensor cores: scores never leave the SM.
 //
-//   CTA            = one (image, head, 128-query tile); 288 threads; TWO CTAs per SM
+//   CTA            = one (image, head, 128-query tile); 160 threads; THREE CTAs per SM
 //   warp 0         = control (one elected lane): TMA producer (Q tile once, K/V blocks of 64 keys through a
-//                    4-slot ring) and MMA issuer:
+//                    2-slot ring) and MMA issuer:
 //                                  S_j = Q K_j^T  (128 x 64 x 64, operands in swizzled smem, fp32 in TMEM)
 //                                  O  += P_j V_j  (128 x 64 x 64, A = P_j read straight from TMEM, B = V_j smem)
-//   warps 1..8     = softmax: two threads per query row (TMEM lane = row; warps 1..4 take key columns 0..31 of a
-//                    block, warps 5..8 columns 32..63, so every SM sub-partition interleaves two softmax warps)
-//   TMEM (256 col) = S/P buffer 0 @0, S/P buffer 1 @80 (80 fp32 columns each), O @160 (64)
+//   warps 1..4     = softmax: ONE thread per query row (TMEM lane = row), so the row maximum and sum need no
+//                    exchange between threads and no barrier
+//   TMEM (128 col) = S/P @0 (64 fp32 columns; P overwrites the first 32 as packed fp16), O @64 (64)
 //
 // What bounds this kernel at head_dim 64 is not the tensor pipe: per 128 x 128 scores the two MMAs take ~512 clk,
 // while reading S out of TMEM once (64 KB at 64 B/clk/SM) and the 16384 exp2 on the 16-lane MUFU take ~1024 clk
-// each.  So every score is read from TMEM exactly ONCE: a thread pulls its 32 scores of a block into registers,
-// the row maximum is exchanged through shared memory, and the probabilities are written back IN PLACE over the
-// scores as packed fp16 (the A operand of the P.V MMA).  Two S buffers let S_{j+1} (and S_{j+2}) run on the tensor
-// pipe while block j is in the softmax; two co-resident CTAs fill each other's remaining bubbles.
+// each, and every block is a serial chain MMA -> TMEM load -> max -> exp2 -> TMEM store -> MMA.  So (a) every
+// score is read from TMEM exactly ONCE (a thread pulls its 64 scores of a block into registers, takes the maximum,
+// exponentiates and writes the probabilities back in place as packed fp16, the A operand of the P.V MMA), and
+// (b) three small CTAs per SM interleave their chains (ncu on the two-CTA version: tensor 16 %, MUFU 33 %, issue
+// 36 % - latency-bound, nothing saturated).
 // The running maximum only moves when a block's maximum exceeds it by more than 2^8 (exponent domain), so the O
 // read-modify-write in TMEM leaves the common path: probabilities stay <= 256 (fp16-exact range), sums are fp32,
 // and the final O / l removes the common factor.
 //
-// 577 tokens = 9 blocks of 64 keys + 1: a remainder of <= 16 keys is folded into the last full block as a fifth
-// 16-key chunk (UMMA N = 80; its K/V rows sit at the head of the next ring slot, contiguous in shared memory), so
-// the CLS-induced "+1" does not cost a block.  Out-of-range rows are zero-filled by TMA (per-image bounds in the
-// tensor map), out-of-range key columns are masked to -inf, 16-key chunks without a key are skipped.
+// Out-of-range rows are zero-filled by TMA (per-image bounds in the tensor map), out-of-range key columns are
+// masked to -inf, 16-key chunks without a key are skipped by the P.V MMAs.
 #include "common.h"
 #include "ptx.cuh"
 #include <stdlib.h>
@@ -33,17 +32,14 @@ namespace owl {
 constexpr int FA_BM = 128;       // queries per CTA
 constexpr int FA_DH = 64;        // head dim
 constexpr int FA_BN = 64;        // keys per block
-constexpr int FA_STAGES = 4;     // K/V ring slots
-constexpr int FA_THREADS = 288;  // control warp + 8 softmax warps
+constexpr int FA_STAGES = 2;     // K/V ring slots
+constexpr int FA_THREADS = 160;  // control warp + 4 softmax warps
+constexpr int FA_CTAS_PER_SM = 3;
 constexpr int FA_Q_BYTES = FA_BM * FA_DH * 2;       // 16 KB
 constexpr int FA_KV_BYTES = FA_BN * FA_DH * 2;      // 8 KB: a multiple of 1024, so every slot stays swizzle-aligned
-constexpr int FA_SMEM = FA_Q_BYTES + 2 * FA_STAGES * FA_KV_BYTES + 1024 + 256 + 2 * 2 * 128 * 4;
-constexpr uint32_t FA_TMEM_COLS = 256;
-constexpr uint32_t FA_TMEM_SW = 80;                 // width of one S/P buffer (64 + the folded 16-key chunk)
-constexpr uint32_t FA_TMEM_O = 2 * FA_TMEM_SW;
-// TMEM column (relative to the S/P buffer) of the packed fp16 probabilities of 16-key chunk c: each softmax half
-// writes inside its own score columns (half 0 owns [0, 32), half 1 owns [32, 80))
-__host__ __device__ constexpr uint32_t fa_p_col(int c) { return c < 2 ? 8u * c : 32u + 8u * (c - 2); }
+constexpr int FA_SMEM = FA_Q_BYTES + 2 * FA_STAGES * FA_KV_BYTES + 1024 + 256;
+constexpr uint32_t FA_TMEM_COLS = 128;
+constexpr uint32_t FA_TMEM_O = 64;
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -83,7 +79,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+__global__ void __launch_bounds__(FA_THREADS, FA_CTAS_PER_SM)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       __half* __restrict__ ctx, int S, int D, float scale_log2, long long* __restrict__ dbg) {
   // dbg (development only): when non-null, CTA (0,0,0) records %globaltimer at phase boundaries
@@ -97,30 +93,25 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + FA_Q_BYTES;                     // ring slots are contiguous: slot s + 1 follows slot s
+  uint8_t* sK = sQ + FA_Q_BYTES;
   uint8_t* sV = sK + FA_STAGES * FA_KV_BYTES;
   uint64_t* kv_full = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_KV_BYTES);
   uint64_t* kv_empty = kv_full + FA_STAGES;
-  uint64_t* s_full = kv_empty + FA_STAGES;   // [2]
-  uint64_t* p_full = s_full + 2;             // [2]
-  uint64_t* o_full = p_full + 2;             // [1]
+  uint64_t* s_full = kv_empty + FA_STAGES;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* xch = reinterpret_cast<float*>(kv_full) + 64;   // [2 block parities][2 halves][128] row max (and final row sum) exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
-  // key blocks: n_full whole blocks; a remainder of <= 16 keys rides on the last whole block (wide tail), unless
-  // that block sits in the last ring slot (its extra rows must be contiguous with it in shared memory)
-  const int n_full = S / FA_BN, rem = S - n_full * FA_BN;
-  const bool wide_tail = rem > 0 && rem <= 16 && n_full >= 1 && (n_full - 1) % FA_STAGES != FA_STAGES - 1;
-  const int n_loads = n_full + (rem > 0 ? 1 : 0);        // K/V blocks of 64 rows fetched
-  const int n_blocks = wide_tail ? n_full : n_loads;     // softmax / MMA iterations
+  const int n_blocks = (S + FA_BN - 1) / FA_BN;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 256); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -146,7 +137,6 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------ control warp: TMA producer + MMA issuer (one elected lane)
     constexpr uint32_t IDESC_S = make_idesc_f16(FA_BM, FA_BN, false, false);
-    constexpr uint32_t IDESC_S_TAIL = make_idesc_f16(FA_BM, FA_BN + 16, false, false);
     constexpr uint32_t IDESC_O = make_idesc_f16(FA_BM, FA_DH, false, true);
     if (lane == 0) {
       const uint32_t aQ = smem_u32(sQ);
@@ -159,175 +149,147 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tma_load_3d(sK + st * FA_KV_BYTES, &tmKV, &kv_full[st], D + h * FA_DH, j * FA_BN, b);
         tma_load_3d(sV + st * FA_KV_BYTES, &tmKV, &kv_full[st], 2 * D + h * FA_DH, j * FA_BN, b);
       };
-      auto issue_s = [&](int j) {   // S_j = Q K_j^T into S buffer j & 1
+      auto issue_s = [&](int j) {   // S_j = Q K_j^T
         const int st = j % FA_STAGES;
-        const bool tail = wide_tail && j == n_blocks - 1;
         mbar_wait(&kv_full[st], (j / FA_STAGES) & 1);
-        if (tail) mbar_wait(&kv_full[st + 1], ((j + 1) / FA_STAGES) & 1);
         tc_fence_after();
         const uint32_t bK = smem_u32(sK + st * FA_KV_BYTES);
-        const uint32_t d = tmem_base + (j & 1) * FA_TMEM_SW;
 #pragma unroll
         for (int k = 0; k < FA_DH / 16; ++k)
-          umma_f16(d, make_sdesc_sw128(aQ + k * 32, 0, 1024), make_sdesc_sw128(bK + k * 32, 0, 1024),
-                   tail ? IDESC_S_TAIL : IDESC_S, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
+          umma_f16(tmem_base, make_sdesc_sw128(aQ + k * 32, 0, 1024), make_sdesc_sw128(bK + k * 32, 0, 1024), IDESC_S,
+                   k > 0 ? 1u : 0u);
+        umma_commit(s_full);
       };
-      while (loaded < FA_STAGES && loaded < n_loads) load_next();
+      while (loaded < FA_STAGES && loaded < n_blocks) load_next();
       issue_s(0);
-      if (n_blocks > 1) issue_s(1);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j % FA_STAGES;
-        const bool tail = wide_tail && j == n_blocks - 1;
-        const int valid = tail ? FA_BN + rem : min(FA_BN, S - j * FA_BN);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        const int valid = min(FA_BN, S - j * FA_BN);
+        mbar_wait(p_full, j & 1);
         tc_fence_after();
         const uint32_t bV = smem_u32(sV + st * FA_KV_BYTES);
-        const uint32_t aP = tmem_base + (j & 1) * FA_TMEM_SW;
         const int nk = (valid + 15) / 16;    // chunks of 16 keys that hold a key
 #pragma unroll
-        for (int k = 0; k < FA_BN / 16 + 1; ++k)
+        for (int k = 0; k < FA_BN / 16; ++k)
           if (k < nk)
-            umma_f16_ts(tmem_base + FA_TMEM_O, aP + fa_p_col(k), make_sdesc_sw128(bV + k * 2048, 8192, 1024), IDESC_O,
+            umma_f16_ts(tmem_base + FA_TMEM_O, tmem_base + 8 * k, make_sdesc_sw128(bV + k * 2048, 8192, 1024), IDESC_O,
                         (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
-        if (tail) umma_commit(&kv_empty[st + 1]);
-        // S_{j+2} reuses this block's buffer: the softmax threads are done with it (they arrived on p_full) and the
-        // tensor pipe executes in order, so it cannot overtake P V_j
-        // (first refill the slot of block j - 1, whose P.V retired long ago: a wide tail needs its extra rows loaded)
-        if (j >= 1 && loaded < n_loads) load_next();
-        if (j + 2 < n_blocks) issue_s(j + 2);
+        // S_{j+1} follows P V_j in issue order: the tensor pipe executes in order, so it cannot overwrite P_j early
+        if (j + 1 < n_blocks) issue_s(j + 1);
+        // refill the slot P V_j is draining (a short wait: that MMA is already running)
+        if (loaded < n_blocks) load_next();
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------ softmax / correction / epilogue: two threads per query row
-    const int quad = warp & 3;                        // TMEM lane quadrant a warp may touch = warp id % 4
-    const int half = (warp - 1) >> 2;                 // 0: key columns [0, 32), 1: [32, 64) (+ the folded chunk)
-    const int row = quad * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    auto sync_softmax = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // ------------------------------------------------ softmax / correction / epilogue: one thread per query row
+    const int row = (warp & 3) * 32 + lane;           // TMEM lane quadrant a warp may touch = warp id % 4
+    const uint32_t sbuf = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t obuf = sbuf + FA_TMEM_O;
     constexpr float kLazy = 8.0f;
+    const bool warp_has_rows = q0 + (warp & 3) * 32 < S;
     float m_run = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n_blocks; ++j) {
-      const bool tail = wide_tail && j == n_blocks - 1;
-      const int valid = tail ? FA_BN + rem : min(FA_BN, S - j * FA_BN);   // key columns of this block that exist
-      const int my_valid = half == 0 ? min(valid, 32) : valid - 32;       // ... among this thread's (<= 0: none)
-      const uint32_t sbuf = tmem_base + lane_addr + (j & 1) * FA_TMEM_SW;
-      float* xj = xch + (j & 1) * 256;   // double-buffered: block j + 1 must not overwrite what a slow partner still reads
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      const int valid = min(FA_BN, S - j * FA_BN);   // key columns of this block that exist
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (threadIdx.x == 64 && j < 6) stamp(2 + 4 * j);
-      // this thread's scores -> registers: the only TMEM read of the block
-      uint32_t r[32], rt[16];
-      if (my_valid > 0) tmem_ld32(sbuf + half * 32, r);
-      if (my_valid > 32) tmem_ld16(sbuf + 64, rt);          // folded chunk (half 1 of a wide tail only)
+      if (!warp_has_rows) {          // last query tile of an image: none of this warp's 32 rows exists (their P / O
+        mbar_arrive(p_full);         // rows stay garbage and are never stored)
+        continue;
+      }
+      // this row's scores -> registers: the only TMEM read of the block
+      uint32_t r[64];
+      tmem_ld32(sbuf, r);
+      if (valid > 32) tmem_ld32(sbuf + 32, r + 32);
       tmem_ld_wait();
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      if (my_valid >= 32) {
+      if (valid == FA_BN) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 64; i += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(r[i]));     mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
         }
-        if (my_valid > 32) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (i >= my_valid - 32) rt[i] = 0xff800000u;
-            mx0 = fmaxf(mx0, __uint_as_float(rt[i]));
-          }
-        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= my_valid) r[i] = 0xff800000u;       // -inf: exp2 -> 0 (also covers "nothing loaded")
+        for (int i = 0; i < 64; ++i) {
+          if (i >= valid) r[i] = 0xff800000u;          // -inf: exp2 -> 0 (also covers the half that was not loaded)
           mx0 = fmaxf(mx0, __uint_as_float(r[i]));
         }
       }
-      xj[half * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      sync_softmax();
-      const float m_blk = fmaxf(xj[row], xj[128 + row]);       // finite: the first key of every block exists
-      // both threads of a row see the same numbers and take the same decision
-      const bool grow = (m_blk - m_run) * scale_log2 > kLazy;   // true for j == 0 (m_run = -inf)
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));   // finite: the first key of every block exists
+      const bool grow = (m_blk - m_run) * scale_log2 > kLazy;         // true for j == 0 (m_run = -inf)
       const float m_new = grow ? m_blk : m_run;
       const float mc = m_new * scale_log2;
       if (threadIdx.x == 64 && j < 6) stamp(3 + 4 * j);
-      // p = exp2(s * c - m * c) as packed fp16, IN PLACE over this thread's own score columns
+      // p = exp2(s * c - m * c) as packed fp16, IN PLACE over the first half of the row's own score columns
       float sum0 = 0.f, sum1 = 0.f;
-      if (my_valid > 0) {
-        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -mc));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -mc));
-          sum0 += p0;
-          sum1 += p1;
-          const __half2 hp = __floats2half2_rn(p0, p1);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
-        }
-        tmem_st16(sbuf + fa_p_col(2 * half), pk);
-        if (my_valid > 32) {
-          uint32_t pt[8];
+      for (int g = 0; g < 2; ++g) {
+        if (g * 32 < valid) {       // warp-uniform
+          uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rt[2 * i]), scale_log2, -mc));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rt[2 * i + 1]), scale_log2, -mc));
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[g * 32 + 2 * i]), scale_log2, -mc));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[g * 32 + 2 * i + 1]), scale_log2, -mc));
             sum0 += p0;
             sum1 += p1;
             const __half2 hp = __floats2half2_rn(p0, p1);
-            pt[i] = *reinterpret_cast<const uint32_t*>(&hp);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
           }
-          tmem_st8(sbuf + fa_p_col(4), pt);
+          tmem_st16(sbuf + g * 16, pk);
         }
       }
       if (threadIdx.x == 64 && j < 6) stamp(4 + 4 * j);
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        // O was accumulated against the old maximum: rescale it once P V_{j-1} has retired (32 columns per half)
+        // O was accumulated against the old maximum: rescale it once P V_{j-1} has retired
         const float alpha = grow ? fast_exp2((m_run - m_new) * scale_log2) : 1.0f;
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-        const uint32_t obuf = tmem_base + lane_addr + FA_TMEM_O + half * 32;
-        uint32_t o[32];
-        tmem_ld32(obuf, o);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st32(obuf, o);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(obuf + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(obuf + c * 32, o);
+        }
         l_run *= alpha;
       }
       l_run += sum0 + sum1;
       m_run = m_new;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
+      mbar_arrive(p_full);
       if (threadIdx.x == 64 && j < 6) stamp(5 + 4 * j);
     }
-    // epilogue: ctx[b, q0 + row, h * 64 + half * 32 ..] = O / l   (l = sum of both halves' partial sums)
+    // epilogue: ctx[b, q0 + row, h * 64 ..] = O / l
     mbar_wait(o_full, (n_blocks - 1) & 1);
     tc_fence_after();
     if (threadIdx.x == 64) stamp(30);
-    sync_softmax();                 // everyone is past the last read of the row-max exchange
-    xch[half * 128 + row] = l_run;
-    sync_softmax();
-    const float inv_l = 1.0f / (xch[row] + xch[128 + row]);
+    const float inv_l = 1.0f / l_run;
     const int q = q0 + row;
-    __half* dst = ctx + (static_cast<long long>(b) * S + q) * D + h * FA_DH + half * 32;
-    const uint32_t obuf = tmem_base + lane_addr + FA_TMEM_O + half * 32;
-    uint32_t o[32];
-    tmem_ld32(obuf, o);
-    tmem_ld_wait();
-    if (q < S) {
+    __half* dst = ctx + (static_cast<long long>(b) * S + q) * D + h * FA_DH;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 v;
-        __half2 t;
-        t = __floats2half2_rn(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l); v.x = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2half2_rn(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l); v.y = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2half2_rn(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l); v.z = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2half2_rn(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l); v.w = *reinterpret_cast<uint32_t*>(&t);
-        *reinterpret_cast<uint4*>(dst + c * 8) = v;
+    for (int c0 = 0; c0 < 2; ++c0) {
+      uint32_t o[32];
+      tmem_ld32(obuf + c0 * 32, o);
+      tmem_ld_wait();
+      if (q < S) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          __half2 t;
+          t = __floats2half2_rn(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l); v.x = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2half2_rn(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l); v.y = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2half2_rn(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l); v.z = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2half2_rn(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l); v.w = *reinterpret_cast<uint32_t*>(&t);
+          *reinterpret_cast<uint4*>(dst + c0 * 32 + c * 8) = v;
+        }
       }
     }
   }
