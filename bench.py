@@ -53,6 +53,16 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_facts():
+    """Per-launch DRAM traffic etc. read from the committed ncu summary (profiles/ncu_facts.json, written by
+    tools/ncu_facts.py from an `ncu --set full` capture of the same kernels at batch 16)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_facts.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -67,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -278,10 +288,31 @@ def run_ours(args):
     k_ms = e0.elapsed_time(e1) / reps
     k_flops = 2.0 * M * cfg.ff * cfg.hidden
     achieved = k_flops / (k_ms * 1e-3) / 1e12
+    ncu = ncu_facts()
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256,K,K,EpiF16<quick_gelu>> (MLP fc1, M=%d N=%d K=%d)" % (M, cfg.ff, cfg.hidden),
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                "traffic": None, "peak_source": pk_kind + " (burst: kernel timed alone)",
+                "traffic": ncu.get("fc1_gemm_dram_bytes") if B == BATCH_PER_GPU else None,
+                "traffic_source": ncu.get("source"), "peak_source": pk_kind + " (burst: kernel timed alone)",
                 "launch_us": k_ms * 1e3, "flops_per_launch": k_flops}
+    # the fused attention kernel (north star: fraction of the attention-GEMM roofline), timed the same way
+    def fa():
+        ops.flash_attn_fwd(ws.qkv, ws.ctx, B=B, S=cfg.tokens, H=cfg.heads, head_dim=cfg.head_dim, scale=cfg.head_dim ** -0.5)
+    for _ in range(3):
+        fa()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fa()
+    e1.record()
+    torch.cuda.synchronize()
+    a_ms = e0.elapsed_time(e1) / reps
+    a_flops = 4.0 * B * cfg.heads * cfg.tokens * cfg.tokens * cfg.head_dim
+    roofline_attn = {"bound": "tensor", "kernel": "flash_attn_fwd_kernel (S=%d, H=%d, dh=%d)" % (cfg.tokens, cfg.heads, cfg.head_dim),
+                     "achieved": a_flops / (a_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": a_flops / (a_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "launch_us": a_ms * 1e3,
+                     "flops_per_launch": a_flops, "traffic": ncu.get("flash_attn_dram_bytes") if B == BATCH_PER_GPU else None,
+                     "tensor_pipe_active_pct_ncu": ncu.get("flash_attn_tensor_pipe_pct"),
+                     "note": "head_dim 64: the MUFU (exp2) and the TMEM read of S each need 2x the MMA cycles, see DESIGN.md"}
     from oracle.owlvit_oracle import flops_per_image  # FLOP accounting only
     fl = flops_per_image(cfg)
     step_tflops = fl["fwd_bwd_ref_policy"] * B / (ms_per_step * 1e-3) / 1e12
@@ -300,7 +331,7 @@ def run_ours(args):
                    "launch": "two CUDA-graph replays per step (fwd+loss+bwd, AdamW)"},
         "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "roofline": roofline, "roofline_step": step_roof, "final_losses": final_losses,
+        "roofline": roofline, "roofline_attention": roofline_attn, "roofline_step": step_roof, "final_losses": final_losses,
     }
 
     if rank == 0 and world == 1 and args.torch_cuda_baseline:

@@ -59,7 +59,9 @@ typedef struct owl_gemm_args {
   long long ldo;
   long long o_outer_stride, o_head_stride; /* elements */
   const float* bias;     /* [N] or NULL */
-  int act;               /* 0 none, 1 quick_gelu, 2 gelu(erf), 3 *= quick_gelu'(act_src), 4 *= gelu'(act_src) */
+  int act;               /* 0 none, 1 quick_gelu, 2 gelu(erf), 3 *= quick_gelu'(act_src), 4 *= gelu'(act_src),
+                            5 exp(v - rowvec[g][m]) (probabilities from a saved log-sum-exp, HF:398),
+                            6 act_src[g][m][n] * (v - rowvec[g][m]) (softmax backward) */
   void* pre_out;         /* fp16, optional: value before the activation (saved for backward) */
   long long ld_pre;
   const void* act_src;   /* fp16 pre-activations for act 3/4 */
@@ -72,6 +74,9 @@ typedef struct owl_gemm_args {
   uint8_t* argmax;       /* epilogue 2: winning prompt variant [M, N/3] */
   const float* alpha_dev; /* optional DEVICE scalar multiplied into alpha (gradient un-scaling without a host sync) */
   int cluster_m;         /* thread-block cluster along M with TMA multicast of the B tile: 0 = auto, 1 = off, 2 = pairs */
+  const float* rowvec;   /* act 5 / 6: fp32 [batches_outer * heads][rowvec_stride], one value per output row */
+  long long rowvec_stride;
+  long long act_src_outer_stride, act_src_head_stride; /* elements; batch offsets of act_src (act 6) */
 } owl_gemm_args;
 
 int owl_gemm(const owl_gemm_args* args, void* stream);
@@ -102,9 +107,15 @@ int owl_softmax_rows_f16(void* scores_f16, long long rows, int n, int ld, void* 
 int owl_cast_f16(const float* src, void* dst_f16, long long n, float scale, void* stream);
 /* HF:379-404 fused attention forward: ctx[b, s, h*64 + d] = softmax(scale * q k^T) v for every (image, head), reading
  * the packed qkv buffer [B*S, 3*H*64] (q | k | v column blocks) and never materialising the scores (tcgen05: S and O
- * accumulate in TMEM, P is fed back to the tensor core from TMEM).  head_dim must be 64. */
-int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, int B, int S, int H, int head_dim, float scale,
+ * accumulate in TMEM, P is fed back to the tensor core from TMEM).  head_dim must be 64.  When lse != NULL it also
+ * stores the natural-log log-sum-exp of the scaled scores, lse[b][h][s] (fp32), from which the backward pass
+ * recomputes the probabilities (owl_gemm act 5). */
+int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse, int B, int S, int H, int head_dim, float scale,
                        void* stream);
+/* Softmax backward row term (autograd of HF:398): delta[b][h][s] = alpha * sum_d dctx[b,s,h*64+d] * ctx[b,s,h*64+d]
+ * (= alpha * sum_j P dP), consumed by owl_gemm act 6. */
+int owl_attn_delta(const void* ctx_f16, const void* dctx_f16, float* delta, int B, int S, int H, int head_dim,
+                   float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Matcher + loss (reference src/matcher.py:85-159, src/losses.py:16-116), device-resident.

@@ -40,6 +40,8 @@ class GemmArgs(ctypes.Structure):
         ("argmax", c_void_p),
         ("alpha_dev", c_void_p),
         ("cluster_m", c_int),
+        ("rowvec", c_void_p), ("rowvec_stride", c_ll),
+        ("act_src_outer_stride", c_ll), ("act_src_head_stride", c_ll),
     ]
 
 

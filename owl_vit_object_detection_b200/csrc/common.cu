@@ -89,4 +89,4 @@ int num_sms() {
 }  // namespace owl
 
 extern "C" const char* owl_last_error(void) { return owl::g_err; }
-extern "C" int owl_abi_version(void) { return 2; }
+extern "C" int owl_abi_version(void) { return 3; }

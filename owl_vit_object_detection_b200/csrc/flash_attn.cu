@@ -81,7 +81,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 __global__ void __launch_bounds__(FA_THREADS, FA_CTAS_PER_SM)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                      __half* __restrict__ ctx, int S, int D, float scale_log2, long long* __restrict__ dbg) {
+                      __half* __restrict__ ctx, float* __restrict__ lse, int S, int D, float scale_log2,
+                      long long* __restrict__ dbg) {
   // dbg (development only): when non-null, CTA (0,0,0) records %globaltimer at phase boundaries
   auto stamp = [&](int slot) {
     if (dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
@@ -273,6 +274,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (threadIdx.x == 64) stamp(30);
     const float inv_l = 1.0f / l_run;
     const int q = q0 + row;
+    // natural-log log-sum-exp of the scaled scores, for the backward pass (probabilities are recomputed from it)
+    if (lse != nullptr && q < S)
+      lse[(static_cast<long long>(b) * gridDim.y + h) * S + q] = (m_run * scale_log2 + log2f(l_run)) * 0.6931471805599453f;
     __half* dst = ctx + (static_cast<long long>(b) * S + q) * D + h * FA_DH;
 #pragma unroll
     for (int c0 = 0; c0 < 2; ++c0) {
@@ -312,6 +316,38 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+// Softmax-backward row term (the "delta" of flash attention): delta[b, h, s] = alpha * sum_d dctx[b, s, h*64 + d] *
+// ctx[b, s, h*64 + d]  (= alpha * sum_j P_sj dP_sj).  One thread per 8 consecutive channels, 8 threads per head.
+__global__ void attn_delta_kernel(const __half* __restrict__ ctx, const __half* __restrict__ dctx,
+                                  float* __restrict__ delta, long long rows, int S, int H, float alpha) {
+  pdl_grid_wait();
+  const long long chunks = rows * H * 8;
+  const long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (i < chunks) {
+    const uint4 a = *reinterpret_cast<const uint4*>(ctx + i * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(dctx + i * 8);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* gh = reinterpret_cast<const __half2*>(&g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = __half22float2(ah[k]), y = __half22float2(gh[k]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (i < chunks && (i & 7) == 0) {
+    const long long rh = i >> 3;              // row * H + head
+    const long long row = rh / H;
+    const int head = static_cast<int>(rh - row * H);
+    const long long bimg = row / S;
+    const int s = static_cast<int>(row - bimg * S);
+    delta[(bimg * H + head) * S + s] = acc * alpha;
+  }
+}
+
 // 3-D fp16 tensor map over the packed QKV buffer: {3*D columns, S rows, B images}
 int make_qkv_map(CUtensorMap* out, const void* qkv, int B, int S, int D, uint32_t box_rows) {
   return make_tensor_map_f16(out, qkv, 3ull * D, static_cast<uint64_t>(S), static_cast<uint64_t>(B), 3ull * D,
@@ -325,8 +361,8 @@ using namespace owl;
 static long long* g_fa_dbg = nullptr;
 extern "C" void owl_flash_attn_debug(long long* dbg) { g_fa_dbg = dbg; }   // development hook, not in the public header
 
-extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, int B, int S, int H, int head_dim, float scale,
-                                  void* stream) {
+extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse, int B, int S, int H, int head_dim,
+                                  float scale, void* stream) {
   OWL_CHECK_ARG(qkv_f16 && ctx_f16 && B > 0 && S > 0 && H > 0, "flash_attn_fwd: bad arguments");
   OWL_CHECK_ARG(head_dim == FA_DH, "flash_attn_fwd: head_dim %d is not built (only 64)", head_dim);
   const int D = H * head_dim;
@@ -343,7 +379,18 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, int B, int
   dim3 grid((S + FA_BM - 1) / FA_BM, H, B);
   const float sl2 = scale * 1.4426950408889634f;
   OWL_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, static_cast<cudaStream_t>(stream), tmQ,
-               tmKV, static_cast<__half*>(ctx_f16), S, D, sl2, g_fa_dbg);
+               tmKV, static_cast<__half*>(ctx_f16), lse, S, D, sl2, g_fa_dbg);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_attn_delta(const void* ctx_f16, const void* dctx_f16, float* delta, int B, int S, int H, int head_dim,
+                              float alpha, void* stream) {
+  OWL_CHECK_ARG(ctx_f16 && dctx_f16 && delta && B > 0 && S > 0 && H > 0, "attn_delta: bad arguments");
+  OWL_CHECK_ARG(head_dim == FA_DH, "attn_delta: head_dim %d is not built (only 64)", head_dim);
+  const long long rows = 1LL * B * S, threads = rows * H * 8;
+  OWL_LAUNCH(attn_delta_kernel, static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream),
+             static_cast<const __half*>(ctx_f16), static_cast<const __half*>(dctx_f16), delta, rows, S, H, alpha);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

@@ -5,6 +5,8 @@ int gemm_launch_kk(const GemmPlan& p, cudaStream_t s) {
   if (p.epilogue == 0) {
     if (p.act == ACT_NONE) { OWL_GEMM_DISPATCH_BN_CM(false, false, EpiF16<ACT_NONE>, p.p16) }
     if (p.act == ACT_QGELU) { OWL_GEMM_DISPATCH_BN_CM(false, false, EpiF16<ACT_QGELU>, p.p16) }
+    if (p.act == ACT_EXP_ROW) { OWL_GEMM_DISPATCH_BN(false, false, EpiF16<ACT_EXP_ROW>, p.p16) }
+    if (p.act == ACT_SMAX_GRAD) { OWL_GEMM_DISPATCH_BN(false, false, EpiF16<ACT_SMAX_GRAD>, p.p16) }
     if (p.act == ACT_GELU) { OWL_GEMM_DISPATCH_BN(false, false, EpiF16<ACT_GELU>, p.p16) }
   }
   if (p.epilogue == 1) { OWL_GEMM_DISPATCH_BN_CM(false, false, EpiF32, p.p32) }

@@ -32,7 +32,8 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
                 "gemm: split_k > 1 needs the fp32 epilogue in atomic mode");
   OWL_CHECK_ARG(a.epilogue != 2 || (a.N % 3 == 0 && a.argmax && !a.a_mn && !a.b_mn && a.batches_outer * a.heads == 1),
                 "gemm: pool3 epilogue needs N %% 3 == 0, K-major operands, no batching and an argmax buffer");
-  OWL_CHECK_ARG(!(a.act == 3 || a.act == 4) || a.act_src, "gemm: act %d needs act_src", a.act);
+  OWL_CHECK_ARG(!(a.act == 3 || a.act == 4 || a.act == 6) || a.act_src, "gemm: act %d needs act_src", a.act);
+  OWL_CHECK_ARG(!(a.act == 5 || a.act == 6) || (a.rowvec && a.rowvec_stride >= a.M), "gemm: act %d needs rowvec", a.act);
 
   GemmPlan& p = *plan;
   p.a_mn = a.a_mn ? 1 : 0;
@@ -44,7 +45,7 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   // 2-CTA clusters (B tile multicast) for the big forward / dgrad GEMMs; args.cluster_m: 0 = auto, 1 = off, 2 = on
   {
     const int mb_ = (a.M + GEMM_BM - 1) / GEMM_BM;
-    const bool eligible = !p.a_mn && p.bn >= 128 && a.epilogue != 2 && a.act != 2 && a.act != 4 && mb_ >= 2;
+    const bool eligible = !p.a_mn && p.bn >= 128 && a.epilogue != 2 && a.act != 2 && a.act < 4 && mb_ >= 2;
     const long long tiles_ = 1LL * mb_ * ((a.N + p.bn - 1) / p.bn) * G * a.split_k;
     if (a.cluster_m == 2) {
       OWL_CHECK_ARG(eligible && !(p.bn == 192 && p.b_mn), "gemm: cluster_m = 2 is not built for this operand layout / epilogue / tile");
@@ -61,8 +62,8 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   }
   OWL_CHECK_ARG(a.epilogue != 2 || a.N <= 256, "gemm: pool3 epilogue supports N <= 256 (got %d)", a.N);
   OWL_CHECK_ARG(!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
-  OWL_CHECK_ARG(!((a.act == 3 || a.act == 4) && a.pre_out), "gemm: act' epilogues cannot also save pre_out");
-  OWL_CHECK_ARG(a.act >= 0 && a.act <= 4 && (a.act == 0 || a.epilogue == 0), "gemm: act %d needs the fp16 epilogue", a.act);
+  OWL_CHECK_ARG(!((a.act == 3 || a.act == 4 || a.act == 6) && a.pre_out), "gemm: act' epilogues cannot also save pre_out");
+  OWL_CHECK_ARG(a.act >= 0 && a.act <= 6 && (a.act == 0 || a.epilogue == 0), "gemm: act %d needs the fp16 epilogue", a.act);
 
   // The third tensor-map dimension enumerates (outer, head) with a common stride when that is
   // expressible; per-head column offsets cover heads packed inside a row (QKV buffer).
@@ -112,12 +113,15 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
     e.pre_out = static_cast<__half*>(a.pre_out);
     e.bias = a.bias;
     e.dact_src = static_cast<const __half*>(a.act_src);
+    e.rowvec = a.rowvec; e.rowvec_stride = a.rowvec_stride;
+    e.d_sb = a.act_src_outer_stride; e.d_sh = a.act_src_head_stride;
     e.ldo = static_cast<int>(a.ldo); e.ld_pre = static_cast<int>(a.ld_pre); e.ld_dact = static_cast<int>(a.ld_act_src);
     e.o_sb = a.o_outer_stride; e.o_sh = a.o_head_stride; e.H = a.heads;
     e.alpha = alpha; e.alpha_dev = a.alpha_dev;
     auto al16 = [](const void* q, long long ld) { return !q || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld * 2) % 16 == 0); };
     e.vec_ok = al16(a.out, a.ldo) && al16(a.pre_out, a.ld_pre) && al16(a.act_src, a.ld_act_src) &&
-               (a.o_outer_stride * 2) % 16 == 0 && (a.o_head_stride * 2) % 16 == 0;
+               (a.o_outer_stride * 2) % 16 == 0 && (a.o_head_stride * 2) % 16 == 0 &&
+               (a.act_src_outer_stride * 2) % 16 == 0 && (a.act_src_head_stride * 2) % 16 == 0;
   } else if (a.epilogue == 1) {
     EpiF32::Params& e = p.p32;
     e.out = static_cast<float*>(a.out);

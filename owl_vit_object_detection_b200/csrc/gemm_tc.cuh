@@ -316,7 +316,10 @@ __device__ __forceinline__ float act_gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-enum : int { ACT_NONE = 0, ACT_QGELU = 1, ACT_GELU = 2, ACT_QGELU_GRAD = 3, ACT_GELU_GRAD = 4 };
+// ACT_EXP_ROW:   v = exp(v - rowvec[g][m])                    (probabilities recomputed from the saved log-sum-exp)
+// ACT_SMAX_GRAD: v = act_src[g][m][n] * (v - rowvec[g][m])      (softmax backward, rowvec = alpha * sum_j P dP)
+enum : int { ACT_NONE = 0, ACT_QGELU = 1, ACT_GELU = 2, ACT_QGELU_GRAD = 3, ACT_GELU_GRAD = 4, ACT_EXP_ROW = 5,
+             ACT_SMAX_GRAD = 6 };
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float v, float src) {
@@ -324,6 +327,7 @@ __device__ __forceinline__ float apply_act(float v, float src) {
   else if constexpr (ACT == ACT_GELU) return act_gelu(v);
   else if constexpr (ACT == ACT_QGELU_GRAD) return v * act_qgelu_grad(src);
   else if constexpr (ACT == ACT_GELU_GRAD) return v * act_gelu_grad(src);
+  else if constexpr (ACT == ACT_SMAX_GRAD) return v * src;
   else return v;
 }
 
@@ -437,6 +441,9 @@ struct EpiF16Params {
   __half* pre_out;
   const float* bias;
   const __half* dact_src;
+  const float* rowvec;   // ACT_EXP_ROW / ACT_SMAX_GRAD: one fp32 per output row, [G][rowvec_stride]
+  long long rowvec_stride;
+  long long d_sb, d_sh;  // element offsets of dact_src per outer batch / head
   int ldo, ld_pre, ld_dact;
   long long o_sb, o_sh;  // element offsets per outer batch / head
   int H;
@@ -464,14 +471,18 @@ struct EpiF16 {
     __half* out = p.out + outer * p.o_sb + head * p.o_sh;
     const bool vec_ok = p.vec_ok != 0;
     const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
-    constexpr bool kGrad = (ACT == ACT_QGELU_GRAD || ACT == ACT_GELU_GRAD);
+    constexpr bool kGrad = (ACT == ACT_QGELU_GRAD || ACT == ACT_GELU_GRAD || ACT == ACT_SMAX_GRAD);
+    constexpr bool kRowVec = (ACT == ACT_EXP_ROW || ACT == ACT_SMAX_GRAD);
     if (row0 >= M) return;  // warp-uniform: nothing of this warp's 32 rows is inside the matrix
+    const __half* dsrc = kGrad ? p.dact_src + outer * p.d_sb + head * p.d_sh : nullptr;
+    float rv = 0.f;         // row phase: thread t owns row t of the warp's 32
+    if constexpr (kRowVec) rv = __ldg(p.rowvec + g * p.rowvec_stride + min(row0 + lane, M - 1));
 #pragma unroll 1
     for (int c = 0; c < (BN + 63) / 64; ++c) {
       const int n = n0 + c * 64;
       if (n >= N) break;  // warp-uniform
       if constexpr (kGrad) {
-        tile_load_f16(p.dact_src, p.ld_dact, row0, n, M, N, stage, lane, vec_ok);
+        tile_load_f16(dsrc, p.ld_dact, row0, n, M, N, stage, lane, vec_ok);
         __syncwarp();
       }
       // pass 0 (only with pre_out): pre-activation values; pass 1: activated values
@@ -489,6 +500,10 @@ struct EpiF16 {
           if (p.bias) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) add_bias4(v + 4 * q, pre.bias, c * 16 + h * 8 + q);
+          }
+          if constexpr (kRowVec) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (ACT == ACT_EXP_ROW) ? __expf(v[i] - rv) : v[i] - rv;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

@@ -14,7 +14,7 @@ Data layout in HBM (B images, S = P + 1 tokens, D hidden):
   residual stream   x      fp32 [B*S, D]   (row = image-major token index, CLS first)
   GEMM operands     *16    fp16, row-major, produced by the LayerNorm / previous GEMM epilogue
   QKV               qkv16  fp16 [B*S, 3D]  (q | k | v column blocks, head h at columns h*dh inside a block)
-  attention probs   fp16 [B*H, S, Sp]      (Sp = S rounded up to 8 so rows are 16-byte aligned for TMA)
+  attention probs   fp16 [B*H, S, Sp]      (backward only, recomputed; Sp = S rounded up to 8: 16-byte rows for TMA)
 """
 from __future__ import annotations
 
@@ -67,7 +67,7 @@ class Workspace:
         self.h1 = z((B * S, D), f16)         # LN1 output (kept for the last layer's wgrad)
         self.h2 = z((B * S, D), f16)         # LN2 output
         self.qkv = z((B * S, 3 * D), f16)
-        self.probs = z((B * H, S, self.Sp), f16)
+        self.lse = z((B * H, S), f32)        # last layer: log-sum-exp of the scaled scores (for the backward)
         self.ctx = z((B * S, D), f16)
         self.m = z((B * S, F), f16)
         self.mpre = z((B * S, F), f16)
@@ -115,8 +115,9 @@ class Workspace:
             b.dmpre = z((B * S, F), f16)
             b.dh32 = z((B * S, D), f32)
             b.dctx = z((B * S, D), f16)
-            b.dprobs32 = z((B * H, S, self.Sp), f32)
+            b.probs = z((B * H, S, self.Sp), f16)      # recomputed from q, k and the saved log-sum-exp
             b.dprobs = z((B * H, S, self.Sp), f16)
+            b.delta = z((B * H, S), f32)
             b.dqkv = z((B * S, 3 * D), f16)
             self._bw = b
         return self._bw
@@ -170,25 +171,12 @@ class Engine:
         return ws
 
     # ------------------------------------------------------------------ forward
-    def _attention(self, ws: Workspace, B: int, keep_probs: bool) -> None:
-        """keep_probs=False: fused tcgen05 attention (scores stay in TMEM).  keep_probs=True (last layer when a
-        backward follows): the probabilities are materialised because dV / dS need them."""
+    def _attention(self, ws: Workspace, B: int, keep_lse: bool) -> None:
+        """Fused tcgen05 attention (HF:379-404): scores stay in TMEM.  keep_lse=True (last layer when a backward
+        follows) also stores the per-row log-sum-exp, from which the backward pass recomputes the probabilities."""
         cfg = self.cfg
-        S, D, H, dh, Sp = cfg.tokens, cfg.hidden, cfg.heads, cfg.head_dim, ws.Sp
-        qkv = ws.qkv
-        if not keep_probs:
-            ops.flash_attn_fwd(qkv, ws.ctx, B=B, S=S, H=H, head_dim=dh, scale=dh ** -0.5)
-            return
-        # scores = (q k^T) / sqrt(dh)   HF:393-396
-        ops.gemm(qkv, qkv[:, D:], ws.probs, M=S, N=S, K=dh, a_ld=3 * D, b_ld=3 * D, ldo=Sp,
-                 batches_outer=B, heads=H, a_outer_stride=S * 3 * D, b_outer_stride=S * 3 * D,
-                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp,
-                 alpha=dh ** -0.5)
-        ops.softmax_rows_f16(ws.probs, rows=B * H * S, n=S, ld=Sp)                      # HF:398
-        # ctx = P v   HF:401, written straight into [B*S, D] (the transpose/reshape of HF:402-403)
-        ops.gemm(ws.probs, qkv[:, 2 * D:], ws.ctx, M=S, N=dh, K=S, b_mn=True, a_ld=Sp, b_ld=3 * D, ldo=D,
-                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
-                 b_outer_stride=S * 3 * D, b_head_col=dh, o_outer_stride=S * D, o_head_stride=dh)
+        ops.flash_attn_fwd(ws.qkv, ws.ctx, B=B, S=cfg.tokens, H=cfg.heads, head_dim=cfg.head_dim,
+                           scale=cfg.head_dim ** -0.5, lse=ws.lse if keep_lse else None)
 
     def forward(self, image: torch.Tensor, save_for_backward: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """image [B,3,IS,IS] fp32 CUDA -> (pred_boxes [B,P,4] xyxy fp32, pred_sims [B,P,C] fp32)."""
@@ -226,7 +214,7 @@ class Engine:
             ops.layernorm(x_in, self.p32(p + "layer_norm1.weight"), self.p32(p + "layer_norm1.bias"), ws.h1,
                           rows=M, D=D, eps=eps)
             ops.gemm(ws.h1, wqkv, ws.qkv, M=M, N=3 * D, K=D, bias=bqkv)
-            self._attention(ws, B, keep_probs=last and save_for_backward)
+            self._attention(ws, B, keep_lse=last and save_for_backward)
             ops.gemm(ws.ctx, self.p16(p + "self_attn.out_proj.weight"), x_mid, M=M, N=D, K=D,
                      bias=self.p32(p + "self_attn.out_proj.bias"), resid=x_in)
             ops.layernorm(x_mid, self.p32(p + "layer_norm2.weight"), self.p32(p + "layer_norm2.bias"), ws.h2,
@@ -349,15 +337,24 @@ class Engine:
         ops.colsum(bw.dx_mid, gview(p + "self_attn.out_proj.bias"), M=M, N=D, gscale=gs)
         ops.gemm(bw.g16, self.p16(p + "self_attn.out_proj.weight"), bw.dctx, M=M, N=D, K=D, b_mn=True)
         qkv, dqkv = ws.qkv, bw.dqkv
+        scale = dh ** -0.5
+        # P = exp(scale q k^T - lse): the probabilities of HF:398, recomputed in the GEMM epilogue
+        ops.gemm(qkv, qkv[:, D:], bw.probs, M=S, N=S, K=dh, a_ld=3 * D, b_ld=3 * D, ldo=Sp,
+                 batches_outer=B, heads=H, a_outer_stride=S * 3 * D, b_outer_stride=S * 3 * D,
+                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp,
+                 alpha=scale, act="exp_row", rowvec=ws.lse, rowvec_stride=S)
         # dV = P^T dctx
-        ops.gemm(ws.probs, bw.dctx, dqkv[:, 2 * D:], M=S, N=dh, K=S, a_mn=True, b_mn=True, a_ld=Sp, b_ld=D, ldo=3 * D,
+        ops.gemm(bw.probs, bw.dctx, dqkv[:, 2 * D:], M=S, N=dh, K=S, a_mn=True, b_mn=True, a_ld=Sp, b_ld=D, ldo=3 * D,
                  batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
                  b_outer_stride=S * D, b_head_col=dh, o_outer_stride=S * 3 * D, o_head_stride=dh)
-        # dP = dctx V^T
-        ops.gemm(bw.dctx, qkv[:, 2 * D:], bw.dprobs32, M=S, N=S, K=dh, a_ld=D, b_ld=3 * D, ldo=Sp,
+        # dS = P * (dctx V^T - sum_j P dP) * scale, the softmax backward fused into the dP GEMM's epilogue;
+        # sum_j P_ij dP_ij = sum_d dctx_id ctx_id (row term computed from the [B*S, D] tensors)
+        ops.attn_delta(ws.ctx, bw.dctx, bw.delta, B=B, S=S, H=H, head_dim=dh, alpha=scale)
+        ops.gemm(bw.dctx, qkv[:, 2 * D:], bw.dprobs, M=S, N=S, K=dh, a_ld=D, b_ld=3 * D, ldo=Sp,
                  batches_outer=B, heads=H, a_outer_stride=S * D, b_outer_stride=S * 3 * D,
-                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp)
-        ops.softmax_bwd_f16(ws.probs, bw.dprobs32, bw.dprobs, rows=B * H * S, n=S, ld=Sp, scale=dh ** -0.5)
+                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp,
+                 alpha=scale, act="softmax_grad", act_src=bw.probs, act_src_outer_stride=H * S * Sp,
+                 act_src_head_stride=S * Sp, rowvec=bw.delta, rowvec_stride=S)
         # dQ = dS K
         ops.gemm(bw.dprobs, qkv[:, D:], dqkv, M=S, N=dh, K=S, b_mn=True, a_ld=Sp, b_ld=3 * D, ldo=3 * D,
                  batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, check, lib, ptr, stream_ptr
 
-ACT = {"none": 0, "quick_gelu": 1, "gelu": 2, "quick_gelu_grad": 3, "gelu_grad": 4}
+ACT = {"none": 0, "quick_gelu": 1, "gelu": 2, "quick_gelu_grad": 3, "gelu_grad": 4, "exp_row": 5, "softmax_grad": 6}
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
@@ -25,7 +25,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          act: str = "none", pre_out: Optional[torch.Tensor] = None, act_src: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None, rows_per_img: int = 0,
          out_mode: int = 0, argmax: Optional[torch.Tensor] = None, pool3: bool = False,
-         alpha_dev: Optional[torch.Tensor] = None, cluster_m: int = 0) -> torch.Tensor:
+         alpha_dev: Optional[torch.Tensor] = None, cluster_m: int = 0, rowvec: Optional[torch.Tensor] = None,
+         rowvec_stride: int = 0, act_src_outer_stride: int = 0, act_src_head_stride: int = 0) -> torch.Tensor:
     """D = alpha * A @ B^T with a fused epilogue; see `struct owl_gemm_args` in include/owl_b200.h."""
     assert a.dtype == torch.float16 and b.dtype == torch.float16 and a.is_cuda and b.is_cuda
     g = GemmArgs()
@@ -64,6 +65,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.argmax = ptr(argmax)
     g.alpha_dev = ptr(alpha_dev)
     g.cluster_m = cluster_m
+    g.rowvec = ptr(rowvec)
+    g.rowvec_stride = rowvec_stride
+    g.act_src_outer_stride, g.act_src_head_stride = act_src_outer_stride, act_src_head_stride
     check(lib().owl_gemm(ctypes.byref(g), ctypes.c_void_p(stream_ptr())), "owl_gemm")
     return out
 
@@ -128,11 +132,28 @@ def softmax_rows_f16(scores: torch.Tensor, *, rows: int, n: int, ld: int):
     return scores
 
 
-def flash_attn_fwd(qkv16: torch.Tensor, ctx16: torch.Tensor, *, B: int, S: int, H: int, head_dim: int, scale: float):
+def flash_attn_fwd(qkv16: torch.Tensor, ctx16: torch.Tensor, *, B: int, S: int, H: int, head_dim: int, scale: float,
+                   lse: Optional[torch.Tensor] = None):
+    """ctx = softmax(scale q k^T) v per (image, head); optionally lse [B, H, S] fp32 (natural log) for the backward."""
     assert qkv16.dtype == torch.float16 and ctx16.dtype == torch.float16 and qkv16.is_contiguous()
-    check(lib().owl_flash_attn_fwd(_vp(qkv16), _vp(ctx16), B, S, H, head_dim, ctypes.c_float(scale), _sp()),
+    if lse is not None:
+        _f32(lse)
+        assert lse.numel() == B * H * S
+    check(lib().owl_flash_attn_fwd(_vp(qkv16), _vp(ctx16), _vp(lse), B, S, H, head_dim, ctypes.c_float(scale), _sp()),
           "owl_flash_attn_fwd")
     return ctx16
+
+
+def attn_delta(ctx16: torch.Tensor, dctx16: torch.Tensor, delta: torch.Tensor, *, B: int, S: int, H: int,
+               head_dim: int, alpha: float):
+    """delta[b, h, s] = alpha * sum_d dctx[b, s, h, d] * ctx[b, s, h, d] (softmax backward row term)."""
+    assert ctx16.dtype == torch.float16 and dctx16.dtype == torch.float16
+    assert ctx16.is_contiguous() and dctx16.is_contiguous()
+    _f32(delta)
+    assert delta.numel() == B * H * S
+    check(lib().owl_attn_delta(_vp(ctx16), _vp(dctx16), _vp(delta), B, S, H, head_dim, ctypes.c_float(alpha), _sp()),
+          "owl_attn_delta")
+    return delta
 
 
 def cast_f16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
