@@ -137,7 +137,8 @@ int owl_lsap(const float* costT, const int* num_targets, int B, int P, int Tmax,
  *   tc_matched [B,P] i64  target_classes as the matcher returns them (background = bg_label)
  *   tc_final   [B,P] i64  after the IoU>0.85 ordered label sweep (src/losses.py:100-106)
  *   pred_sorted / tgt_sorted [B,Tmax] i64  the matcher's `indices` (sorted by prediction), -1 padded
- *   losses_per_image [B,4], losses_mean4 [4]  (loss_ce, loss_bg, loss_bbox, loss_giou)
+ *   losses_per_image [B,64] (per-image workspace; [b][0..3] = loss_ce, loss_bg, loss_bbox, loss_giou on return),
+ *   losses_mean4 [4]  (the same four, mean over images)
  *   dsims_unit [B,P,C], dl1 / dgiou [B,Tmax,4]  gradients for unit upstream grads, incl. the 1/B of the mean */
 int owl_match_loss(const float* sims, const float* boxes, const long long* labels, const float* tboxes,
                    const int* num_targets, const int* match_pred, const float* scales, int B, int P, int C,

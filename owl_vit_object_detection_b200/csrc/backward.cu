@@ -202,14 +202,18 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, int M, int 
   const int m1 = min(M, m0 + 256);
   float a = 0.f, b = 0.f;
   if (c < N) {
-    for (int m = m0 + threadIdx.y; m < m1; m += 8) {
-      if constexpr (sizeof(T) == 2) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(x + m * ld + c));
-        a += f.x; b += f.y;
-      } else {
-        const float2 f = *reinterpret_cast<const float2*>(x + m * ld + c);
-        a += f.x; b += f.y;
+    // eight rows in flight per thread (the loads of a batch are issued before the first add)
+    for (int m = m0 + threadIdx.y; m < m1; m += 64) {
+      float2 f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int mm = min(m + 8 * k, M - 1);
+        if constexpr (sizeof(T) == 2) f[k] = __half22float2(*reinterpret_cast<const __half2*>(x + mm * ld + c));
+        else f[k] = *reinterpret_cast<const float2*>(x + mm * ld + c);
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (m + 8 * k < m1) { a += f[k].x; b += f[k].y; }
     }
   }
   red[threadIdx.y][threadIdx.x * 2] = a;
@@ -264,70 +268,71 @@ __global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __
 // accumulators in shared memory; one set of global atomics per CTA.
 constexpr int LNB_WARPS = 4;
 
+template <int NV>
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ dy, long long dy_stride,
               const float* __restrict__ gamma, const float* __restrict__ dx_add, float* __restrict__ dx,
-              long long dx_stride, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D, float eps,
+              long long dx_stride, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, float eps,
               int rows_per_cta, const float* __restrict__ gscale) {
+  constexpr int D = NV * 128;
   pdl_grid_wait();
   extern __shared__ float lnb_sm[];  // [LNB_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nv = D >> 7;
   float* accg = lnb_sm + (warp * 2) * D;
   float* accb = accg + D;
   for (int i = lane; i < 2 * D; i += 32) accg[i] = 0.f;
+  float4 gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
   __syncwarp();
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   for (int row = r0 + warp; row < r1; row += LNB_WARPS) {
-    float4 xv[BW_MAX_VEC], gv[BW_MAX_VEC];
+    // all of the row's loads are issued before the first use (in-order issue would expose a latency per load)
+    float4 xv[NV], gv[NV], av[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const float4*>(x + row * x_stride + i * 128 + lane * 4);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) gv[i] = *reinterpret_cast<const float4*>(dy + row * dy_stride + i * 128 + lane * 4);
+    if (dx_add) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) av[i] = *reinterpret_cast<const float4*>(dx_add + row * dx_stride + i * 128 + lane * 4);
+    }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        xv[i] = *reinterpret_cast<const float4*>(x + row * x_stride + i * 128 + lane * 4);
-        gv[i] = *reinterpret_cast<const float4*>(dy + row * dy_stride + i * 128 + lane * 4);
-        s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
-      }
+    for (int i = 0; i < NV; ++i) s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
     const float mean = bw_warp_sum(s) / D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
-        q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
-      }
+    for (int i = 0; i < NV; ++i) {
+      xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+      q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+    }
     const float rstd = rsqrtf(bw_warp_sum(q) / D + eps);
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        const int c = i * 128 + lane * 4;
-        xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;   // xh
-        float4 a = *reinterpret_cast<float4*>(accg + c), b = *reinterpret_cast<float4*>(accb + c);
-        a.x += gv[i].x * xv[i].x; a.y += gv[i].y * xv[i].y; a.z += gv[i].z * xv[i].z; a.w += gv[i].w * xv[i].w;
-        b.x += gv[i].x; b.y += gv[i].y; b.z += gv[i].z; b.w += gv[i].w;
-        *reinterpret_cast<float4*>(accg + c) = a;
-        *reinterpret_cast<float4*>(accb + c) = b;
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        gv[i].x *= gm.x; gv[i].y *= gm.y; gv[i].z *= gm.z; gv[i].w *= gm.w;   // g = dy * gamma
-        sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
-        sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
-      }
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 128 + lane * 4;
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;   // xh
+      float4 a = *reinterpret_cast<float4*>(accg + c), b = *reinterpret_cast<float4*>(accb + c);
+      a.x += gv[i].x * xv[i].x; a.y += gv[i].y * xv[i].y; a.z += gv[i].z * xv[i].z; a.w += gv[i].w * xv[i].w;
+      b.x += gv[i].x; b.y += gv[i].y; b.z += gv[i].z; b.w += gv[i].w;
+      *reinterpret_cast<float4*>(accg + c) = a;
+      *reinterpret_cast<float4*>(accb + c) = b;
+      gv[i].x *= gm[i].x; gv[i].y *= gm[i].y; gv[i].z *= gm[i].z; gv[i].w *= gm[i].w;   // g = dy * gamma
+      sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+    }
     if (dx) {
       const float mg = bw_warp_sum(sg) / D, mgx = bw_warp_sum(sgx) / D;
 #pragma unroll
-      for (int i = 0; i < BW_MAX_VEC; ++i)
-        if (i < nv) {
-          const int c = i * 128 + lane * 4;
-          float4 o;
-          o.x = rstd * (gv[i].x - mg - xv[i].x * mgx); o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
-          o.z = rstd * (gv[i].z - mg - xv[i].z * mgx); o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
-          if (dx_add) {
-            const float4 a = *reinterpret_cast<const float4*>(dx_add + row * dx_stride + c);
-            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-          }
-          *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
-        }
+      for (int i = 0; i < NV; ++i) {
+        const int c = i * 128 + lane * 4;
+        float4 o;
+        o.x = rstd * (gv[i].x - mg - xv[i].x * mgx); o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
+        o.z = rstd * (gv[i].z - mg - xv[i].z * mgx); o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
+        if (dx_add) { o.x += av[i].x; o.y += av[i].y; o.z += av[i].z; o.w += av[i].w; }
+        *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
+      }
     }
   }
   __syncthreads();
@@ -344,16 +349,17 @@ ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
 // ------------------------------------------------------------------ backward of reference src/models.py:80-86
 // feats = LN2(LN1(x_p) * cl),  cl = LN1(x_cls).  Given dfeats (fp32, scaled): dx for the patch rows,
 // dcl[b] (atomic, scaled), and the four LayerNorm parameter gradients (atomic, un-scaled).
+template <int NV>
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 post_fuse_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ecls, const float* __restrict__ g1,
                      const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ dfeats,
                      float* __restrict__ dx, float* __restrict__ dcl, float* __restrict__ dg1, float* __restrict__ db1,
-                     float* __restrict__ dg2, float* __restrict__ db2, int P, int D, float eps, int rows_per_cta,
+                     float* __restrict__ dg2, float* __restrict__ db2, int P, float eps, int rows_per_cta,
                      const float* __restrict__ gscale) {
+  constexpr int D = NV * 128;
   pdl_grid_wait();
   extern __shared__ float pf_sm[];  // [LNB_WARPS][5][D]: dg2, db2, dcl, dg1, db1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nv = D >> 7;
   const int b = blockIdx.y;
   float* acc = pf_sm + warp * 5 * D;
   for (int i = lane; i < 5 * D; i += 32) acc[i] = 0.f;
@@ -363,99 +369,94 @@ post_fuse_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ecls
   for (int p = p0 + warp; p < p1; p += LNB_WARPS) {
     const float* xr = x + (1LL * b * (P + 1) + 1 + p) * D;
     const float* dyr = dfeats + (1LL * b * P + p) * D;
-    float4 xh[BW_MAX_VEC], uh[BW_MAX_VEC], g[BW_MAX_VEC];
+    // the row's loads are issued before the first use (in-order issue would expose a latency per load)
+    float4 xh[NV], uh[NV], g[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xh[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) g[i] = *reinterpret_cast<const float4*>(dyr + i * 128 + lane * 4);   // dy for now
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        xh[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
-        s += (xh[i].x + xh[i].y) + (xh[i].z + xh[i].w);
-      }
+    for (int i = 0; i < NV; ++i) s += (xh[i].x + xh[i].y) + (xh[i].z + xh[i].w);
     float mean = bw_warp_sum(s) / D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        xh[i].x -= mean; xh[i].y -= mean; xh[i].z -= mean; xh[i].w -= mean;
-        q += (xh[i].x * xh[i].x + xh[i].y * xh[i].y) + (xh[i].z * xh[i].z + xh[i].w * xh[i].w);
-      }
+    for (int i = 0; i < NV; ++i) {
+      xh[i].x -= mean; xh[i].y -= mean; xh[i].z -= mean; xh[i].w -= mean;
+      q += (xh[i].x * xh[i].x + xh[i].y * xh[i].y) + (xh[i].z * xh[i].z + xh[i].w * xh[i].w);
+    }
     const float rstd1 = rsqrtf(bw_warp_sum(q) / D + eps);
     s = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        const int c = i * 128 + lane * 4;
-        xh[i].x *= rstd1; xh[i].y *= rstd1; xh[i].z *= rstd1; xh[i].w *= rstd1;
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(g1 + c));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(b1 + c));
-        const float4 cl = __ldg(reinterpret_cast<const float4*>(cr + c));
-        uh[i].x = (xh[i].x * gm.x + be.x) * cl.x; uh[i].y = (xh[i].y * gm.y + be.y) * cl.y;
-        uh[i].z = (xh[i].z * gm.z + be.z) * cl.z; uh[i].w = (xh[i].w * gm.w + be.w) * cl.w;
-        s += (uh[i].x + uh[i].y) + (uh[i].z + uh[i].w);
-      }
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 128 + lane * 4;
+      xh[i].x *= rstd1; xh[i].y *= rstd1; xh[i].z *= rstd1; xh[i].w *= rstd1;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(g1 + c));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(b1 + c));
+      const float4 cl = __ldg(reinterpret_cast<const float4*>(cr + c));
+      uh[i].x = (xh[i].x * gm.x + be.x) * cl.x; uh[i].y = (xh[i].y * gm.y + be.y) * cl.y;
+      uh[i].z = (xh[i].z * gm.z + be.z) * cl.z; uh[i].w = (xh[i].w * gm.w + be.w) * cl.w;
+      s += (uh[i].x + uh[i].y) + (uh[i].z + uh[i].w);
+    }
     mean = bw_warp_sum(s) / D;
     q = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        uh[i].x -= mean; uh[i].y -= mean; uh[i].z -= mean; uh[i].w -= mean;
-        q += (uh[i].x * uh[i].x + uh[i].y * uh[i].y) + (uh[i].z * uh[i].z + uh[i].w * uh[i].w);
-      }
+    for (int i = 0; i < NV; ++i) {
+      uh[i].x -= mean; uh[i].y -= mean; uh[i].z -= mean; uh[i].w -= mean;
+      q += (uh[i].x * uh[i].x + uh[i].y * uh[i].y) + (uh[i].z * uh[i].z + uh[i].w * uh[i].w);
+    }
     const float rstd2 = rsqrtf(bw_warp_sum(q) / D + eps);
     float sg = 0.f, sgu = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        const int c = i * 128 + lane * 4;
-        uh[i].x *= rstd2; uh[i].y *= rstd2; uh[i].z *= rstd2; uh[i].w *= rstd2;
-        const float4 dy = *reinterpret_cast<const float4*>(dyr + c);
-        float4 a = *reinterpret_cast<float4*>(acc + c), bb = *reinterpret_cast<float4*>(acc + D + c);
-        a.x += dy.x * uh[i].x; a.y += dy.y * uh[i].y; a.z += dy.z * uh[i].z; a.w += dy.w * uh[i].w;
-        bb.x += dy.x; bb.y += dy.y; bb.z += dy.z; bb.w += dy.w;
-        *reinterpret_cast<float4*>(acc + c) = a;
-        *reinterpret_cast<float4*>(acc + D + c) = bb;
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(g2 + c));
-        g[i].x = dy.x * gm.x; g[i].y = dy.y * gm.y; g[i].z = dy.z * gm.z; g[i].w = dy.w * gm.w;
-        sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        sgu += (g[i].x * uh[i].x + g[i].y * uh[i].y) + (g[i].z * uh[i].z + g[i].w * uh[i].w);
-      }
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 128 + lane * 4;
+      uh[i].x *= rstd2; uh[i].y *= rstd2; uh[i].z *= rstd2; uh[i].w *= rstd2;
+      const float4 dy = g[i];
+      float4 a = *reinterpret_cast<float4*>(acc + c), bb = *reinterpret_cast<float4*>(acc + D + c);
+      a.x += dy.x * uh[i].x; a.y += dy.y * uh[i].y; a.z += dy.z * uh[i].z; a.w += dy.w * uh[i].w;
+      bb.x += dy.x; bb.y += dy.y; bb.z += dy.z; bb.w += dy.w;
+      *reinterpret_cast<float4*>(acc + c) = a;
+      *reinterpret_cast<float4*>(acc + D + c) = bb;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(g2 + c));
+      g[i].x = dy.x * gm.x; g[i].y = dy.y * gm.y; g[i].z = dy.z * gm.z; g[i].w = dy.w * gm.w;
+      sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      sgu += (g[i].x * uh[i].x + g[i].y * uh[i].y) + (g[i].z * uh[i].z + g[i].w * uh[i].w);
+    }
     float mg = bw_warp_sum(sg) / D, mgx = bw_warp_sum(sgu) / D;
     sg = 0.f; sgu = 0.f;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        const int c = i * 128 + lane * 4;
-        // du
-        float4 du;
-        du.x = rstd2 * (g[i].x - mg - uh[i].x * mgx); du.y = rstd2 * (g[i].y - mg - uh[i].y * mgx);
-        du.z = rstd2 * (g[i].z - mg - uh[i].z * mgx); du.w = rstd2 * (g[i].w - mg - uh[i].w * mgx);
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(g1 + c));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(b1 + c));
-        const float4 cl = __ldg(reinterpret_cast<const float4*>(cr + c));
-        float4 a = *reinterpret_cast<float4*>(acc + 2 * D + c);          // dcl += du * t
-        a.x += du.x * (xh[i].x * gm.x + be.x); a.y += du.y * (xh[i].y * gm.y + be.y);
-        a.z += du.z * (xh[i].z * gm.z + be.z); a.w += du.w * (xh[i].w * gm.w + be.w);
-        *reinterpret_cast<float4*>(acc + 2 * D + c) = a;
-        float4 dt = make_float4(du.x * cl.x, du.y * cl.y, du.z * cl.z, du.w * cl.w);
-        float4 ag = *reinterpret_cast<float4*>(acc + 3 * D + c), ab = *reinterpret_cast<float4*>(acc + 4 * D + c);
-        ag.x += dt.x * xh[i].x; ag.y += dt.y * xh[i].y; ag.z += dt.z * xh[i].z; ag.w += dt.w * xh[i].w;
-        ab.x += dt.x; ab.y += dt.y; ab.z += dt.z; ab.w += dt.w;
-        *reinterpret_cast<float4*>(acc + 3 * D + c) = ag;
-        *reinterpret_cast<float4*>(acc + 4 * D + c) = ab;
-        g[i].x = dt.x * gm.x; g[i].y = dt.y * gm.y; g[i].z = dt.z * gm.z; g[i].w = dt.w * gm.w;   // dxh
-        sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        sgu += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-      }
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 128 + lane * 4;
+      // du
+      float4 du;
+      du.x = rstd2 * (g[i].x - mg - uh[i].x * mgx); du.y = rstd2 * (g[i].y - mg - uh[i].y * mgx);
+      du.z = rstd2 * (g[i].z - mg - uh[i].z * mgx); du.w = rstd2 * (g[i].w - mg - uh[i].w * mgx);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(g1 + c));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(b1 + c));
+      const float4 cl = __ldg(reinterpret_cast<const float4*>(cr + c));
+      float4 a = *reinterpret_cast<float4*>(acc + 2 * D + c);          // dcl += du * t
+      a.x += du.x * (xh[i].x * gm.x + be.x); a.y += du.y * (xh[i].y * gm.y + be.y);
+      a.z += du.z * (xh[i].z * gm.z + be.z); a.w += du.w * (xh[i].w * gm.w + be.w);
+      *reinterpret_cast<float4*>(acc + 2 * D + c) = a;
+      float4 dt = make_float4(du.x * cl.x, du.y * cl.y, du.z * cl.z, du.w * cl.w);
+      float4 ag = *reinterpret_cast<float4*>(acc + 3 * D + c), ab = *reinterpret_cast<float4*>(acc + 4 * D + c);
+      ag.x += dt.x * xh[i].x; ag.y += dt.y * xh[i].y; ag.z += dt.z * xh[i].z; ag.w += dt.w * xh[i].w;
+      ab.x += dt.x; ab.y += dt.y; ab.z += dt.z; ab.w += dt.w;
+      *reinterpret_cast<float4*>(acc + 3 * D + c) = ag;
+      *reinterpret_cast<float4*>(acc + 4 * D + c) = ab;
+      g[i].x = dt.x * gm.x; g[i].y = dt.y * gm.y; g[i].z = dt.z * gm.z; g[i].w = dt.w * gm.w;   // dxh
+      sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      sgu += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+    }
     mg = bw_warp_sum(sg) / D; mgx = bw_warp_sum(sgu) / D;
     float* dxr = dx + (1LL * b * (P + 1) + 1 + p) * D;
 #pragma unroll
-    for (int i = 0; i < BW_MAX_VEC; ++i)
-      if (i < nv) {
-        float4 o;
-        o.x = rstd1 * (g[i].x - mg - xh[i].x * mgx); o.y = rstd1 * (g[i].y - mg - xh[i].y * mgx);
-        o.z = rstd1 * (g[i].z - mg - xh[i].z * mgx); o.w = rstd1 * (g[i].w - mg - xh[i].w * mgx);
-        *reinterpret_cast<float4*>(dxr + i * 128 + lane * 4) = o;
-      }
+    for (int i = 0; i < NV; ++i) {
+      float4 o;
+      o.x = rstd1 * (g[i].x - mg - xh[i].x * mgx); o.y = rstd1 * (g[i].y - mg - xh[i].y * mgx);
+      o.z = rstd1 * (g[i].z - mg - xh[i].z * mgx); o.w = rstd1 * (g[i].w - mg - xh[i].w * mgx);
+      *reinterpret_cast<float4*>(dxr + i * 128 + lane * 4) = o;
+    }
   }
   __syncthreads();
   const float us = gscale[1];
@@ -596,10 +597,19 @@ extern "C" int owl_layernorm_bwd(const float* x, long long x_stride, const float
   OWL_CHECK_ARG(x && dy && gamma && dgamma && dbeta && rows > 0, "layernorm_bwd: bad arguments");
   OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * BW_MAX_VEC, "layernorm_bwd: unsupported D = %d", D);
   OWL_CHECK_ARG(!dx_add || dx, "layernorm_bwd: dx_add needs dx");
-  const int rows_per_cta = rows >= 148 * 16 ? 32 : (rows >= 148 * 4 ? 8 : 4);
+  const int rows_per_cta = rows >= 148 * 16 ? 16 : (rows >= 148 * 4 ? 8 : 4);
   const size_t smem = sizeof(float) * LNB_WARPS * 2 * D;
-  OWL_LAUNCH(ln_bwd_kernel, (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream), 
-      x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma, dbeta, rows, D, eps, rows_per_cta, gscale);
+#define OWL_LNB_CASE(NV)                                                                                              \
+  case NV:                                                                                                            \
+    OWL_LAUNCH(ln_bwd_kernel<NV>, (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem,                     \
+               static_cast<cudaStream_t>(stream), x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma,  \
+               dbeta, rows, eps, rows_per_cta, gscale);                                                               \
+    break;
+  switch (D / 128) {
+    OWL_LNB_CASE(1) OWL_LNB_CASE(2) OWL_LNB_CASE(3) OWL_LNB_CASE(4) OWL_LNB_CASE(5) OWL_LNB_CASE(6) OWL_LNB_CASE(7)
+    OWL_LNB_CASE(8)
+  }
+#undef OWL_LNB_CASE
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
@@ -610,16 +620,25 @@ extern "C" int owl_post_fuse_bwd(const float* x, const float* ecls, const float*
   OWL_CHECK_ARG(x && ecls && g1 && b1 && g2 && dfeats && dx && dcl && dg1 && db1 && dg2 && db2 && gscale && B > 0 && P > 0,
                 "post_fuse_bwd: bad arguments");
   OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * BW_MAX_VEC, "post_fuse_bwd: unsupported D = %d", D);
-  const int rows_per_cta = 48;
+  const int rows_per_cta = 24;
   const size_t smem = sizeof(float) * LNB_WARPS * 5 * D;
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    OWL_CUDA(cudaFuncSetAttribute(post_fuse_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
   dim3 grid((P + rows_per_cta - 1) / rows_per_cta, B);
-  OWL_LAUNCH(post_fuse_bwd_kernel, grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream), 
-      x, ecls, g1, b1, g2, dfeats, dx, dcl, dg1, db1, dg2, db2, P, D, eps, rows_per_cta, gscale);
+#define OWL_PFB_CASE(NV)                                                                                             \
+  case NV: {                                                                                                         \
+    static bool configured = false;                                                                                  \
+    if (!configured) {                                                                                               \
+      OWL_CUDA(cudaFuncSetAttribute(post_fuse_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                    static_cast<int>(smem)));                                                        \
+      configured = true;                                                                                             \
+    }                                                                                                                \
+    OWL_LAUNCH(post_fuse_bwd_kernel<NV>, grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream), x, ecls, g1, \
+               b1, g2, dfeats, dx, dcl, dg1, db1, dg2, db2, P, eps, rows_per_cta, gscale);                          \
+  } break;
+  switch (D / 128) {
+    OWL_PFB_CASE(1) OWL_PFB_CASE(2) OWL_PFB_CASE(3) OWL_PFB_CASE(4) OWL_PFB_CASE(5) OWL_PFB_CASE(6) OWL_PFB_CASE(7)
+    OWL_PFB_CASE(8)
+  }
+#undef OWL_PFB_CASE
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

@@ -403,6 +403,10 @@ lsap_block_kernel(const float* __restrict__ costT, const int* __restrict__ num_t
 // K13 + K14: CTA per image.
 // =====================================================================================================
 constexpr int LOSS_THREADS = 256;
+constexpr int LOSS_CHUNKS = 24;   // row slices per image in the class-loss kernel
+constexpr int LOSS_WS = 64;       // floats of per-image workspace: [0..3] ce, bg, bbox, giou; [4] #positive rows;
+                                  // [8 + 2 c + {0,1}] class-loss partial sums of row slice c
+static_assert(8 + 2 * LOSS_CHUNKS <= LOSS_WS, "loss workspace");
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
@@ -558,53 +562,101 @@ match_loss_kernel(const float* __restrict__ sims, const float* __restrict__ boxe
   }
   atomicAdd(&s_npos, npos_local);
   __syncthreads();
-  const int npos = s_npos, nbg = P - npos;
-  const float inv_pos = 1.0f / static_cast<float>(npos), inv_bg = 1.0f / static_cast<float>(nbg);
+  if (tid == 0) {
+    float* L = losses + 1LL * b * LOSS_WS;
+    L[2] = l1_sum * inv_t;
+    L[3] = gi_sum * inv_t;
+    L[4] = static_cast<float>(s_npos);      // exact: P < 2^24
+  }
+}
 
-  // ---- class loss + gradient (reference src/losses.py:16-40; BCELoss on |sim| with class weights) -----
+// ---- class loss + gradient (reference src/losses.py:16-40; BCELoss on |sim| with class weights) ---------------
+// Grid (LOSS_CHUNKS, B): a CTA owns a slice of an image's prediction rows, a warp one row at a time.  A row's
+// similarities are all fetched before the first is used (the SM issues in order; one CTA per image with a load per
+// loop iteration spent 130 us on exposed latencies).  Partial sums go to the per-image workspace; loss_reduce_kernel
+// adds them in a fixed order, so the result is deterministic.
+constexpr int LOSS_MAXC_PER_LANE = 8;   // C <= 256
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+class_loss_kernel(const float* __restrict__ sims, const long long* __restrict__ tc_final,
+                  const float* __restrict__ scales, int P, int C, int bg, float* __restrict__ losses,
+                  float* __restrict__ dsims, float inv_batch) {
+  pdl_grid_wait();
+  __shared__ float red[8];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* L = losses + 1LL * b * LOSS_WS;
+  const int npos = static_cast<int>(L[4]), nbg = P - npos;
+  const float inv_pos = 1.0f / static_cast<float>(npos), inv_bg = 1.0f / static_cast<float>(nbg);
+  const int rows = (P + LOSS_CHUNKS - 1) / LOSS_CHUNKS;
+  const int p0 = chunk * rows, p1 = min(P, p0 + rows);
+  float w[LOSS_MAXC_PER_LANE];
+#pragma unroll
+  for (int k = 0; k < LOSS_MAXC_PER_LANE; ++k) {
+    const int c = lane + 32 * k;
+    w[k] = (scales && c < C) ? __ldg(scales + c) : 1.0f;
+  }
   float ce_acc = 0.f, bg_acc = 0.f;
-  for (int p = warp; p < P; p += LOSS_THREADS / 32) {
-    const int lab = tc[p];
-    const bool pos = lab != bg;
-    const float rscale = (pos ? inv_pos : inv_bg) * inv_batch;
+  for (int p = p0 + warp; p < p1; p += LOSS_THREADS / 32) {
     const float* srow = sims + (1LL * b * P + p) * C;
     float* drow = dsims + (1LL * b * P + p) * C;
+    float sv[LOSS_MAXC_PER_LANE];
+#pragma unroll
+    for (int k = 0; k < LOSS_MAXC_PER_LANE; ++k) {
+      const int c = lane + 32 * k;
+      sv[k] = c < C ? srow[c] : 0.f;
+    }
+    const int lab = static_cast<int>(tc_final[1LL * b * P + p]);
+    const bool pos = lab != bg;
+    const float rscale = (pos ? inv_pos : inv_bg) * inv_batch;
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float s = srow[c];
-      const float q = fabsf(s);
-      const float y = (pos && c == lab) ? 1.0f : 0.0f;
-      const float w = scales ? scales[c] : 1.0f;
-      // torch BCE: (y - 1) * max(log1p(-q), -100) - y * max(log(q), -100), times weight
-      const float l = ((y - 1.0f) * fmaxf(log1pf(-q), -100.0f) - y * fmaxf(logf(q), -100.0f)) * w;
-      const float e = expf(-l);
-      const float om = 1.0f - e;
-      acc += om * om * l;
-      // d/dl [(1-e^-l)^2 l] = 2 (1-e^-l) e^-l l + (1-e^-l)^2 ; dl/dq = w (q - y) / max((1-q) q, 1e-12)
-      const float dfdl = 2.0f * om * e * l + om * om;
-      const float dldq = w * (q - y) / fmaxf((1.0f - q) * q, 1e-12f);
-      const float sgn = s > 0.f ? 1.0f : (s < 0.f ? -1.0f : 0.0f);
-      drow[c] = dfdl * dldq * sgn * rscale;
+#pragma unroll
+    for (int k = 0; k < LOSS_MAXC_PER_LANE; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) {
+        const float s = sv[k];
+        const float q = fabsf(s);
+        const float y = (pos && c == lab) ? 1.0f : 0.0f;
+        // torch BCE: (y - 1) * max(log1p(-q), -100) - y * max(log(q), -100), times weight
+        const float l = ((y - 1.0f) * fmaxf(log1pf(-q), -100.0f) - y * fmaxf(logf(q), -100.0f)) * w[k];
+        const float e = expf(-l);
+        const float om = 1.0f - e;
+        acc += om * om * l;
+        // d/dl [(1-e^-l)^2 l] = 2 (1-e^-l) e^-l l + (1-e^-l)^2 ; dl/dq = w (q - y) / max((1-q) q, 1e-12)
+        const float dfdl = 2.0f * om * e * l + om * om;
+        const float dldq = w[k] * (q - y) / fmaxf((1.0f - q) * q, 1e-12f);
+        const float sgn = s > 0.f ? 1.0f : (s < 0.f ? -1.0f : 0.0f);
+        drow[c] = dfdl * dldq * sgn * rscale;
+      }
     }
     if (pos) ce_acc += acc; else bg_acc += acc;
   }
   const float ce_sum = block_sum(ce_acc, red);
   const float bg_sum = block_sum(bg_acc, red);
-  if (tid == 0) {
-    losses[4 * b + 0] = ce_sum * inv_pos;    // mean over positive rows (NaN if none, like the reference)
-    losses[4 * b + 1] = bg_sum * inv_bg;
-    losses[4 * b + 2] = l1_sum * inv_t;
-    losses[4 * b + 3] = gi_sum * inv_t;
+  if (threadIdx.x == 0) {
+    L[8 + 2 * chunk] = ce_sum;
+    L[8 + 2 * chunk + 1] = bg_sum;
   }
 }
 
-// mean over images, fixed order (deterministic)
-__global__ void loss_reduce_kernel(const float* __restrict__ per_image, int B, float* __restrict__ out4) {
+// per image: class losses from the chunk partials (fixed order); then the mean over images (fixed order)
+__global__ void loss_reduce_kernel(float* __restrict__ per_image, int B, int P, float* __restrict__ out4) {
   pdl_grid_wait();
   const int k = threadIdx.x;
+  if (k < 2) {
+    for (int b = 0; b < B; ++b) {
+      float* L = per_image + 1LL * b * LOSS_WS;
+      float s = 0.f;
+      for (int c = 0; c < LOSS_CHUNKS; ++c) s += L[8 + 2 * c + k];
+      const float npos = L[4];
+      // mean over positive / background rows (NaN if there are none, like the reference)
+      L[k] = s * (1.0f / (k == 0 ? npos : static_cast<float>(P) - npos));
+    }
+  }
+  __syncwarp();
   if (k < 4) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += per_image[4 * b + k];
+    for (int b = 0; b < B; ++b) s += per_image[1LL * b * LOSS_WS + k];
     out4[k] = s / static_cast<float>(B);
   }
 }
@@ -703,6 +755,7 @@ extern "C" int owl_match_loss(const float* sims, const float* boxes, const long 
                     pred_sorted && tgt_sorted && losses_per_image && losses_mean4 && dsims_unit && dl1 && dgiou,
                 "match_loss: null argument");
   OWL_CHECK_ARG(B > 0 && P > 0 && C > 0 && Tmax > 0, "match_loss: empty dimension");
+  OWL_CHECK_ARG(C <= 32 * LOSS_MAXC_PER_LANE, "match_loss: C = %d classes (max %d)", C, 32 * LOSS_MAXC_PER_LANE);
   const size_t smem = sizeof(float) * 4 * P + sizeof(int) * P + sizeof(float) * 8;
   OWL_CHECK_ARG(smem <= 200 * 1024, "match_loss: P = %d too large", P);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -715,7 +768,10 @@ extern "C" int owl_match_loss(const float* sims, const float* boxes, const long 
                                                   Tmax, bg_label, tc_matched, tc_final, pred_sorted, tgt_sorted,
                                                   losses_per_image, dsims_unit, dl1, dgiou, 1.0f / B);
   OWL_CUDA(cudaGetLastError());
-  OWL_LAUNCH(loss_reduce_kernel, 1, 32, 0, s, losses_per_image, B, losses_mean4);
+  OWL_LAUNCH(class_loss_kernel, dim3(LOSS_CHUNKS, B), LOSS_THREADS, 0, s, sims, tc_final, scales, P, C, bg_label,
+             losses_per_image, dsims_unit, 1.0f / B);
+  OWL_CUDA(cudaGetLastError());
+  OWL_LAUNCH(loss_reduce_kernel, 1, 32, 0, s, losses_per_image, B, P, losses_mean4);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

@@ -28,7 +28,7 @@ class _Buffers:
         self.tc_final = torch.zeros((B, P), dtype=i64, device=dev)
         self.pred_sorted = torch.zeros((B, Tmax), dtype=i64, device=dev)
         self.tgt_sorted = torch.zeros((B, Tmax), dtype=i64, device=dev)
-        self.losses_per_image = torch.zeros((B, 4), dtype=f32, device=dev)
+        self.losses_per_image = torch.zeros((B, ops.LOSS_WS), dtype=f32, device=dev)   # [:, :4] = the four losses
         self.dsims_unit = torch.zeros((B, P, C), dtype=f32, device=dev)
         self.dl1 = torch.zeros((B, Tmax, 4), dtype=f32, device=dev)
         self.dgiou = torch.zeros((B, Tmax, 4), dtype=f32, device=dev)

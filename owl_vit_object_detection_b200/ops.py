@@ -184,14 +184,18 @@ def lsap(costT, num_targets, match_pred, status):
     return match_pred
 
 
+LOSS_WS = 64   # floats of per-image workspace owl_match_loss needs ([:, :4] = ce, bg, bbox, giou on return)
+
+
 def match_loss(sims, boxes, labels, tboxes, num_targets, match_pred, scales, bg_label, *, tc_matched, tc_final,
                pred_sorted, tgt_sorted, losses_per_image, losses_mean4, dsims_unit, dl1, dgiou):
     B, P, C = sims.shape
+    assert losses_per_image.is_contiguous() and losses_per_image.numel() >= B * LOSS_WS
     Tmax = labels.shape[1]
     check(lib().owl_match_loss(_vp(sims), _vp(boxes), _vp(labels), _vp(tboxes), _vp(num_targets), _vp(match_pred),
                                _vp(scales), B, P, C, Tmax, bg_label, _vp(tc_matched), _vp(tc_final),
                                _vp(pred_sorted), _vp(tgt_sorted), _vp(losses_per_image), _vp(losses_mean4),
-                               _vp(dsims_unit), _vp(dl1), _vp(dgiou), _sp()), "owl_match_loss", kernels=2)
+                               _vp(dsims_unit), _vp(dl1), _vp(dgiou), _sp()), "owl_match_loss", kernels=3)
 
 
 def loss_backward(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, bg_label, dsims, dboxes):

@@ -96,7 +96,7 @@ def test_b32_train_step_grads_vs_reference_golden(golden_dir):
         tc_final=torch.zeros((B, P), dtype=torch.int64, device=dev),
         pred_sorted=torch.zeros((B, Tmax), dtype=torch.int64, device=dev),
         tgt_sorted=torch.zeros((B, Tmax), dtype=torch.int64, device=dev),
-        losses_per_image=torch.zeros((B, 4), device=dev), losses_mean4=torch.zeros(4, device=dev),
+        losses_per_image=torch.zeros((B, ops.LOSS_WS), device=dev), losses_mean4=torch.zeros(4, device=dev),
         dsims_unit=torch.zeros((B, P, C), device=dev), dl1=torch.zeros((B, Tmax, 4), device=dev),
         dgiou=torch.zeros((B, Tmax, 4), device=dev))
     ops.match_loss(sims, boxes, labels, tboxes, nt, match, scales, C, **out)
