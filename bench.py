@@ -184,7 +184,18 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     cfg = synth.B32
@@ -235,7 +246,6 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -265,6 +275,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world * args.steps / (t.item() * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (value and e2e)
 
     # ---------------- roofline of the dominant kernel (the MLP fc1 tcgen05 GEMM, bias + quick_gelu epilogue),
     # timed live with CUDA events on the launching stream

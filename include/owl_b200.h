@@ -118,6 +118,17 @@ int owl_attn_delta(const void* ctx_f16, const void* dctx_f16, float* delta, int 
                    float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Detection post-processing (reference src/models.py:122-146 `PostProcess`, eval path main.py:110-118): per image,
+ * best class per prediction (first maximum), score > confidence_threshold, class-aware NMS exactly as
+ * torchvision.ops.batched_nms's coordinate-trick path on the CPU (stable descending score order, fp32 IoU compared
+ * with a double threshold).  boxes [B,P,4] f32 xyxy, sims [B,P,C] f32 -> the survivors of image b, in decreasing
+ * score order, in out_boxes[b][0..count) / out_classes[b][..] (i64) / out_scores[b][..]; out_count [B] i32.
+ * One CTA per image; the reference is batch-1 only. */
+int owl_postprocess(const float* boxes, const float* sims, int B, int P, int C, float confidence_threshold,
+                    double iou_threshold, float* out_boxes, long long* out_classes, float* out_scores, int* out_count,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Matcher + loss (reference src/matcher.py:85-159, src/losses.py:16-116), device-resident.
  * Targets are padded: labels [B,Tmax] i64, tboxes [B,Tmax,4] f32 xyxy, num_targets [B] i32.
  * `status` is a device int, OR-ed with 1 for a degenerate box (the reference asserts, src/matcher.py:34-35)

@@ -206,6 +206,23 @@ def loss_backward(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, bg_la
           "owl_loss_backward")
 
 
+def postprocess(boxes: torch.Tensor, sims: torch.Tensor, confidence_threshold: float, iou_threshold: float):
+    """reference src/models.py:122-146 for a whole batch on the device: returns (out_boxes [B,P,4], out_classes
+    [B,P] i64, out_scores [B,P], count [B] i32); the first count[b] rows of image b are its detections."""
+    _f32(boxes), _f32(sims)
+    B, P, C = sims.shape
+    assert boxes.shape == (B, P, 4)
+    dev = sims.device
+    out_boxes = torch.zeros((B, P, 4), dtype=torch.float32, device=dev)
+    out_classes = torch.zeros((B, P), dtype=torch.int64, device=dev)
+    out_scores = torch.zeros((B, P), dtype=torch.float32, device=dev)
+    count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    check(lib().owl_postprocess(_vp(boxes), _vp(sims), B, P, C, ctypes.c_float(confidence_threshold),
+                                ctypes.c_double(iou_threshold), _vp(out_boxes), _vp(out_classes), _vp(out_scores),
+                                _vp(count), _sp()), "owl_postprocess")
+    return out_boxes, out_classes, out_scores, count
+
+
 # ------------------------------------------------------------------------------------------ backward kernels
 def _ll(v: int) -> ctypes.c_longlong:
     return ctypes.c_longlong(v)

@@ -209,3 +209,37 @@ def subsample(t: torch.Tensor) -> torch.Tensor:
         return t
     t2 = t.reshape(-1, t.shape[-1]) if t.dim() > 1 else t.reshape(-1, 1)
     return t2[::37, ::29]
+
+
+# ------------------------------------------------------------------------------------------ PostProcess cases
+# name -> (confidence_threshold, iou_threshold); inputs from make_postprocess_inputs(name)
+POSTPROCESS_CASES = {
+    "dense": (0.01, 0.6),      # reference config.yaml thresholds: almost every prediction passes, NMS does the work
+    "ties": (0.2, 0.5),        # quantised scores / duplicated boxes: stable-sort and first-maximum tie rules
+    "sparse": (0.75, 0.3),     # PostProcess defaults: few or no survivors (image 2 has none)
+}
+
+
+def make_postprocess_inputs(name: str, n_images: int = 3, patches: int = 576, n_classes: int = 80, seed: int = 6):
+    """(pred_boxes [B,P,4] xyxy in [0,1], pred_sims [B,P,C]) for the PostProcess parity cases: boxes jittered around
+    a few dozen centres so that class-aware NMS has real work, a handful of dominant classes."""
+    g = _gen(seed, "postprocess_" + name)
+    centres = 0.15 + 0.7 * torch.rand((n_images, 40, 2), generator=g)
+    sizes = 0.05 + 0.3 * torch.rand((n_images, 40, 2), generator=g)
+    which = torch.randint(0, 40, (n_images, patches), generator=g)
+    cxy = torch.gather(centres, 1, which[..., None].expand(-1, -1, 2)) + 0.02 * torch.randn((n_images, patches, 2), generator=g)
+    wh = torch.gather(sizes, 1, which[..., None].expand(-1, -1, 2)) * (1 + 0.1 * torch.randn((n_images, patches, 2), generator=g))
+    wh = wh.clamp_min(0.01)
+    lo = (cxy - wh / 2).clamp(0.0, 1.0)
+    hi = torch.maximum((cxy + wh / 2).clamp(0.0, 1.0), lo + 1e-3)
+    boxes = torch.cat([lo, hi], dim=-1).float()
+    sims = torch.rand((n_images, patches, n_classes), generator=g) * 0.2 - 0.1
+    hot = torch.randint(0, 6, (n_images, patches), generator=g)                  # six dominant classes
+    boost = torch.rand((n_images, patches), generator=g)
+    sims.scatter_(2, hot[..., None], boost[..., None])
+    if name == "ties":
+        sims = torch.round(sims * 16) / 16
+        boxes[:, 1::7] = boxes[:, 0:-1:7][:, : boxes[:, 1::7].shape[1]]          # exact duplicates
+    if name == "sparse":
+        sims[2] = sims[2].clamp_max(0.5)                                          # nothing above 0.75 in image 2
+    return boxes.contiguous(), sims.float().contiguous()

@@ -8,21 +8,28 @@ from owl_vit_object_detection_b200.synth import trainable_names
 
 
 class PostProcess:
-    """reference src/models.py:122-146 (eval only, batch 1; SURVEY §8f row N2 — not on the accelerated path):
-    best class per prediction, confidence threshold, class-aware NMS."""
+    """reference src/models.py:122-146 (eval path, main.py:110-118): best class per prediction, confidence threshold,
+    class-aware NMS, survivors in decreasing-score order - one `owl_postprocess` launch (CTA per image) instead of
+    boolean-mask indexing and torchvision's batched_nms.  Same call signature and return shapes as the reference
+    (batch 1: boxes [1,K,4], classes [1,K] i64, scores [1,K]); `batched` returns the padded per-image results."""
 
     def __init__(self, confidence_threshold=0.75, iou_threshold=0.3):
         self.confidence_threshold = confidence_threshold
         self.iou_threshold = iou_threshold
 
+    def batched(self, all_pred_boxes, pred_classes):
+        """[B,P,4], [B,P,C] -> (boxes [B,P,4], classes [B,P], scores [B,P], count [B]) on the device, no sync."""
+        from owl_vit_object_detection_b200 import ops
+        if not all_pred_boxes.is_cuda:
+            raise RuntimeError("PostProcess runs on the CUDA device only (there is no CPU fallback)")
+        return ops.postprocess(all_pred_boxes.detach().float().contiguous(), pred_classes.detach().float().contiguous(),
+                               self.confidence_threshold, self.iou_threshold)
+
     def __call__(self, all_pred_boxes, pred_classes):
-        from torchvision.ops import batched_nms
-        boxes, sims = all_pred_boxes[0], pred_classes[0]
-        scores, classes = sims.max(dim=1)
-        keep = scores > self.confidence_threshold
-        boxes, scores, classes = boxes[keep], scores[keep], classes[keep]
-        keep = batched_nms(boxes, scores, classes, iou_threshold=self.iou_threshold)
-        return boxes[keep][None], classes[keep][None], scores[keep][None]
+        assert all_pred_boxes.shape[0] == 1, "the reference PostProcess is batch-1 (use .batched for more)"
+        boxes, classes, scores, count = self.batched(all_pred_boxes, pred_classes)
+        k = int(count[0].item())            # the reference syncs here too (boolean-mask indexing)
+        return boxes[:, :k], classes[:, :k], scores[:, :k]
 
 
 def load_model(labelmap, device):
