@@ -37,7 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 16 for b32, 4 for l14)")
+    ap.add_argument("--workload", default="b32", choices=["b32", "l14"],
+                    help="b32 = BASELINE.json configs[1] (the metric's configuration); l14 = configs[3], OWL-ViT-L/14 "
+                         "840x840, batch 4 per GPU (an extension over the reference, SURVEY D5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-cuda-baseline", action="store_true",
                     help="also time the fp32 torch-CUDA restatement of the reference step (stock-path denominator)")
@@ -198,8 +201,10 @@ def run_ours(args):
             os.close(saved_stdout)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    cfg = synth.B32
-    B = args.batch
+    cfg = synth.B32 if args.workload == "b32" else synth.L14
+    B = args.batch or (BATCH_PER_GPU if args.workload == "b32" else 4)
+    workload = WORKLOAD if args.workload == "b32" else WORKLOAD.replace("B/32", "L/14").replace("768x768", "840x840")
+    metric = METRIC if args.workload == "b32" else METRIC.replace("B/32 768px", "L/14 840px")
     sd = synth.make_weights(cfg, seed=0)
     model = OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg, device=dev)
     del sd
@@ -302,7 +307,7 @@ def run_ours(args):
     ncu = ncu_facts()
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256,K,K,EpiF16<quick_gelu>> (MLP fc1, M=%d N=%d K=%d)" % (M, cfg.ff, cfg.hidden),
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                "traffic": ncu.get("fc1_gemm_dram_bytes") if B == BATCH_PER_GPU else None,
+                "traffic": ncu.get("fc1_gemm_dram_bytes") if (B == BATCH_PER_GPU and args.workload == "b32") else None,
                 "traffic_source": ncu.get("source"), "peak_source": pk_kind + " (burst: kernel timed alone)",
                 "launch_us": k_ms * 1e3, "flops_per_launch": k_flops}
     # the fused attention kernel (north star: fraction of the attention-GEMM roofline), timed the same way
@@ -321,7 +326,7 @@ def run_ours(args):
     roofline_attn = {"bound": "tensor", "kernel": "flash_attn_fwd_kernel (S=%d, H=%d, dh=%d)" % (cfg.tokens, cfg.heads, cfg.head_dim),
                      "achieved": a_flops / (a_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": a_flops / (a_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "launch_us": a_ms * 1e3,
-                     "flops_per_launch": a_flops, "traffic": ncu.get("flash_attn_dram_bytes") if B == BATCH_PER_GPU else None,
+                     "flops_per_launch": a_flops, "traffic": ncu.get("flash_attn_dram_bytes") if (B == BATCH_PER_GPU and args.workload == "b32") else None,
                      "tensor_pipe_active_pct_ncu": ncu.get("flash_attn_tensor_pipe_pct"),
                      "note": "head_dim 64: the MUFU (exp2) and the TMEM read of S each need 2x the MMA cycles, see DESIGN.md"}
     from oracle.owlvit_oracle import flops_per_image  # FLOP accounting only
@@ -332,13 +337,13 @@ def run_ours(args):
                  "attention_gemm_flops_per_image": fl["attn_core"] * cfg.layers}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+        "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}" + (" (NCCL all-reduce of one flat fp32 grad buffer)" if world > 1 else ""),
                    "precision": "fp16 operands, fp32 accumulate / residual / master weights",
-                   "l2": f"{n_slots} rotating input batches (340 MB) + >1 GB of activations per step exceed the 126 MB L2",
+                   "l2": f"{n_slots} rotating input batches ({n_slots * h2d >> 20} MB) + >1 GB of activations per step exceed the 126 MB L2",
                    "launch": "two CUDA-graph replays per step (fwd+loss+bwd, AdamW)"},
         "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -347,7 +352,7 @@ def run_ours(args):
 
     if rank == 0 and world == 1 and args.torch_cuda_baseline:
         line["torch_cuda_baseline"] = torch_cuda_baseline(B)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "b32":
         del step, model
         torch.cuda.empty_cache()
         sec, cores = oracle_cpu_step_time(2, iters=3, warmup=1)
