@@ -118,6 +118,17 @@ int owl_attn_delta(const void* ctx_f16, const void* dctx_f16, float* delta, int 
                    float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Image preprocessing (reference src/dataset.py:64-71 -> HF OwlViTImageProcessor of the pinned transformers 4.30.2:
+ * PIL bicubic resize to out_size x out_size, rescale 1/255, CLIP mean / std, channels first), on raw uint8 pixels.
+ * img_hwc [H][W][3] u8 RGB on the DEVICE (row_stride_bytes between rows), lut [3][256] f32 = value of channel c for
+ * byte v (host-computed with the reference's op sequence), out_chw [3][out_size][out_size] f32.  The resample is
+ * Pillow's ImagingResample bit for bit (integer coefficients with 22 fraction bits, horizontal pass then vertical
+ * pass, each rounded to uint8).  workspace: owl_preprocess_workspace_bytes(H, W, out_size) bytes, 16-byte aligned. */
+long long owl_preprocess_workspace_bytes(int H, int W, int out_size);
+int owl_preprocess_image(const uint8_t* img_hwc, int H, int W, long long row_stride_bytes, const float* lut,
+                         float* out_chw, int out_size, void* workspace, long long workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Detection post-processing (reference src/models.py:122-146 `PostProcess`, eval path main.py:110-118): per image,
  * best class per prediction (first maximum), score > confidence_threshold, class-aware NMS exactly as
  * torchvision.ops.batched_nms's coordinate-trick path on the CPU (stable descending score order, fp32 IoU compared

@@ -109,6 +109,7 @@ class OwlViT(nn.Module):
         self._flat_grad: Optional[torch.Tensor] = None
         self._engine: Optional[Engine] = None
         self._anchor = None
+        self._pre = None            # DevicePreprocessor, created on the first uint8 input
         self._names = list(self.layout.shapes)
         train = set(trainable_names(cfg))
         for name in self._names:
@@ -219,6 +220,14 @@ class OwlViT(nn.Module):
             raise ValueError(f"expected [B,3,H,W], got {tuple(image.shape)}")
         if image.device != self._flat.device:
             raise RuntimeError(f"image on {image.device}, model on {self._flat.device}")
+        if image.dtype == torch.uint8:
+            # raw RGB pixels [B,H,W,3]: the reference's CPU preprocessing (src/dataset.py:64-71) runs on the device
+            if image.shape[3] != 3:
+                raise ValueError(f"uint8 input must be raw RGB [B,H,W,3], got {tuple(image.shape)}")
+            if self._pre is None:
+                from .preprocess import DevicePreprocessor
+                self._pre = DevicePreprocessor(self.cfg.image_size, self._flat.device)
+            image = self._pre(list(image))
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             self._check_policy()

@@ -206,6 +206,26 @@ def loss_backward(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, bg_la
           "owl_loss_backward")
 
 
+def preprocess_workspace_bytes(H: int, W: int, out_size: int) -> int:
+    fn = lib().owl_preprocess_workspace_bytes
+    fn.restype = ctypes.c_longlong
+    return int(fn(H, W, out_size))
+
+
+def preprocess_image(img_hwc: torch.Tensor, lut: torch.Tensor, out_chw: torch.Tensor, workspace: torch.Tensor):
+    """uint8 [H,W,3] CUDA (rows may be strided) -> out_chw [3,S,S] fp32: Pillow-exact bicubic resize + the lut."""
+    assert img_hwc.is_cuda and img_hwc.dtype == torch.uint8 and img_hwc.dim() == 3 and img_hwc.shape[2] == 3
+    assert img_hwc.stride(2) == 1 and img_hwc.stride(1) == 3, "pixels must be packed RGB"
+    _f32(lut), _f32(out_chw)
+    assert lut.numel() == 768 and out_chw.dim() == 3 and out_chw.shape[0] == 3 and out_chw.shape[1] == out_chw.shape[2]
+    assert workspace.dtype == torch.uint8 and workspace.is_cuda
+    H, W = int(img_hwc.shape[0]), int(img_hwc.shape[1])
+    check(lib().owl_preprocess_image(_vp(img_hwc), H, W, ctypes.c_longlong(img_hwc.stride(0)), _vp(lut), _vp(out_chw),
+                                     int(out_chw.shape[1]), _vp(workspace), ctypes.c_longlong(workspace.numel()), _sp()),
+          "owl_preprocess_image", kernels=4)
+    return out_chw
+
+
 def postprocess(boxes: torch.Tensor, sims: torch.Tensor, confidence_threshold: float, iou_threshold: float):
     """reference src/models.py:122-146 for a whole batch on the device: returns (out_boxes [B,P,4], out_classes
     [B,P] i64, out_scores [B,P], count [B] i32); the first count[b] rows of image b are its detections."""

@@ -243,3 +243,21 @@ def make_postprocess_inputs(name: str, n_images: int = 3, patches: int = 576, n_
     if name == "sparse":
         sims[2] = sims[2].clamp_max(0.5)                                          # nothing above 0.75 in image 2
     return boxes.contiguous(), sims.float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------ preprocessing cases
+# (height, width, output size): COCO-like down-scaling, up-scaling, identity on one axis, odd sizes, strong reduction
+PREPROCESS_CASES = [(480, 640, 768), (427, 640, 768), (333, 500, 768), (768, 1024, 768), (1200, 1600, 768),
+                    (97, 131, 768), (2001, 1503, 768), (64, 48, 96)]
+
+
+def make_raw_image(h: int, w: int, seed: int = 0):
+    """Synthetic uint8 RGB image [h, w, 3] (numpy): smooth gradients + blocks + noise, so that resampling sees both
+    flat regions and edges."""
+    import numpy as np
+    rng = np.random.default_rng(1000 + seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([127 + 120 * np.sin(xx / (7.0 + seed)) * np.cos(yy / 11.0), 255.0 * xx / max(w - 1, 1),
+                     255.0 * ((xx // 16 + yy // 16) % 2)], axis=-1)
+    noise = rng.integers(-40, 41, size=(h, w, 3))
+    return np.clip(base + noise, 0, 255).astype(np.uint8)
