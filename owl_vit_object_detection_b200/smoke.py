@@ -44,6 +44,21 @@ def run(verbose: bool = True) -> None:
     g = model.flat_grad
     assert torch.isfinite(g).all() and g.abs().max().item() > 0, "gradients missing / not finite"
     assert not torch.equal(before, model.flat_trainable), "optimizer step did not change the parameters"
+    # eval-side rows: PostProcess (src/models.py:122-146) and device preprocessing (src/dataset.py:64-71), bit-exact
+    import numpy as np
+    from oracle import postprocess_oracle as po   # checker only
+    from oracle import preprocess_oracle as pre   # checker only
+    from . import ops
+    from .preprocess import DevicePreprocessor
+    pb, ps = synth.make_postprocess_inputs("dense", n_images=1)
+    ob, oc, osc, cnt = ops.postprocess(pb.cuda(), ps.cuda(), 0.01, 0.6)
+    rb2, rc2, rs2 = po.postprocess_image(pb[0].numpy(), ps[0].numpy(), 0.01, 0.6)
+    k = int(cnt[0])
+    assert k == rc2.shape[0] and np.array_equal(oc[0, :k].cpu().numpy(), rc2) and \
+        np.array_equal(ob[0, :k].cpu().numpy(), rb2), "postprocess mismatch vs oracle"
+    raw = synth.make_raw_image(60, 80, seed=1)
+    px = DevicePreprocessor(cfg.image_size, "cuda:0")([torch.from_numpy(raw)])[0].cpu().numpy()
+    assert np.array_equal(px, pre.preprocess(raw, cfg.image_size)), "preprocess mismatch vs oracle"
     if verbose:
         print(f"smoke ok: forward err boxes {eb:.1e} sims {es:.1e}; losses "
               + ", ".join(f"{k}={v.item():.4f}" for k, v in losses.items())
