@@ -3,7 +3,7 @@
 //
 //   CTA            = one (image, head, 128-query tile); 160 threads; THREE CTAs per SM
 //   warp 0         = control (one elected lane): TMA producer (Q tile once, K/V blocks of 64 keys through a
-//                    2-slot ring) and MMA issuer:
+//                    3-slot ring) and MMA issuer:
 //                                  S_j = Q K_j^T  (128 x 64 x 64, operands in swizzled smem, fp32 in TMEM)
 //                                  O  += P_j V_j  (128 x 64 x 64, A = P_j read straight from TMEM, B = V_j smem)
 //   warps 1..4     = softmax: ONE thread per query row (TMEM lane = row), so the row maximum and sum need no
@@ -32,7 +32,7 @@ namespace owl {
 constexpr int FA_BM = 128;       // queries per CTA
 constexpr int FA_DH = 64;        // head dim
 constexpr int FA_BN = 64;        // keys per block
-constexpr int FA_STAGES = 2;     // K/V ring slots
+constexpr int FA_STAGES = 3;     // K/V ring slots (2 left the load of block j + 1 exposed: 0.6 us per block)
 constexpr int FA_THREADS = 160;  // control warp + 4 softmax warps
 constexpr int FA_CTAS_PER_SM = 3;
 constexpr int FA_Q_BYTES = FA_BM * FA_DH * 2;       // 16 KB
@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(FA_THREADS, FA_CTAS_PER_SM)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       __half* __restrict__ ctx, float* __restrict__ lse, int S, int D, float scale_log2,
                       long long* __restrict__ dbg) {
-  // dbg (development only): when non-null, CTA (0,0,0) records %globaltimer at phase boundaries
+  // Development instrumentation (make FA_TIMELINE=1, tools/fa_timeline.py): CTA (0,0,0) records %globaltimer at phase
+  // boundaries, every CTA its start / end / SM.  Compiled out by default: it keeps loop counters in vector registers.
+#ifdef OWL_FA_TIMELINE
   auto stamp = [&](int slot) {
     if (dbg != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
       long long t;
@@ -91,6 +93,10 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       dbg[slot] = t;
     }
   };
+#else
+  auto stamp = [](int) {};
+  (void)dbg;
+#endif
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -128,60 +134,74 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (threadIdx.x == 64) stamp(0);
   pdl_grid_wait();   // set-up above overlaps the previous kernel's tail
   if (threadIdx.x == 64) stamp(1);
+#ifdef OWL_FA_TIMELINE
   if (dbg != nullptr && threadIdx.x == 64) {
     const long long cta = blockIdx.x + gridDim.x * (blockIdx.y + 1LL * gridDim.y * blockIdx.z);
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     dbg[64 + 3 * cta] = t;
   }
+#endif
 
   if (warp == 0) {
-    // ------------------------------------------------ control warp: TMA producer + MMA issuer (one elected lane)
+    // ------------------------------------------------ control warp: TMA producer + MMA issuer.
+    // The whole warp walks the loop with warp-uniform state and ONE ELECTED lane issues (elect.sync): the tcgen05 /
+    // TMA operands then stay in uniform registers.  Issuing from inside `if (lane == 0)` made ptxas move every
+    // operand through R2UR, and building the descriptors per MMA did the rest: 0.6 us to issue 8 MMAs, on the
+    // critical path of every block.  Descriptors are built once; a K step only adds to their address field.
     constexpr uint32_t IDESC_S = make_idesc_f16(FA_BM, FA_BN, false, false);
     constexpr uint32_t IDESC_O = make_idesc_f16(FA_BM, FA_DH, false, true);
-    if (lane == 0) {
-      const uint32_t aQ = smem_u32(sQ);
-      int loaded = 0;
-      auto load_next = [&]() {   // K/V rows [64 * loaded, +64) -> ring slot loaded % STAGES (+ the Q tile with block 0)
-        const int j = loaded++, st = j % FA_STAGES;
-        mbar_wait(&kv_empty[st], ((j / FA_STAGES) & 1) ^ 1);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);          // provably warp-uniform for ptxas
+    const uint64_t dQ = make_sdesc_sw128(smem_u32(sQ), 0, 1024);           // + k * (32 >> 4) per K step of 16
+    const uint64_t dK0 = make_sdesc_sw128(smem_u32(sK), 0, 1024);          // + slot * (KV_BYTES >> 4), + k * 2
+    const uint64_t dV0 = make_sdesc_sw128(smem_u32(sV), 8192, 1024);       // + slot * (KV_BYTES >> 4), + k * (2048 >> 4)
+    int loaded = 0;
+    auto load_next = [&]() {   // K/V rows [64 * loaded, +64) -> ring slot loaded % STAGES (+ the Q tile with block 0)
+      const int j = loaded++, st = j % FA_STAGES;
+      mbar_wait(&kv_empty[st], ((j / FA_STAGES) & 1) ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * FA_KV_BYTES + (j == 0 ? FA_Q_BYTES : 0));
         if (j == 0) tma_load_3d(sQ, &tmQ, &kv_full[st], h * FA_DH, q0, b);
         tma_load_3d(sK + st * FA_KV_BYTES, &tmKV, &kv_full[st], D + h * FA_DH, j * FA_BN, b);
         tma_load_3d(sV + st * FA_KV_BYTES, &tmKV, &kv_full[st], 2 * D + h * FA_DH, j * FA_BN, b);
-      };
-      auto issue_s = [&](int j) {   // S_j = Q K_j^T
-        const int st = j % FA_STAGES;
-        mbar_wait(&kv_full[st], (j / FA_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t bK = smem_u32(sK + st * FA_KV_BYTES);
+      }
+      __syncwarp();
+    };
+    auto issue_s = [&](int j) {   // S_j = Q K_j^T
+      const int st = j % FA_STAGES;
+      mbar_wait(&kv_full[st], (j / FA_STAGES) & 1);
+      tc_fence_after();
+      const uint64_t dK = dK0 + static_cast<uint64_t>(st * (FA_KV_BYTES >> 4));
+      if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < FA_DH / 16; ++k)
-          umma_f16(tmem_base, make_sdesc_sw128(aQ + k * 32, 0, 1024), make_sdesc_sw128(bK + k * 32, 0, 1024), IDESC_S,
-                   k > 0 ? 1u : 0u);
+        for (int k = 0; k < FA_DH / 16; ++k) umma_f16(tmem_u, dQ + 2 * k, dK + 2 * k, IDESC_S, k > 0 ? 1u : 0u);
         umma_commit(s_full);
-      };
-      while (loaded < FA_STAGES && loaded < n_blocks) load_next();
-      issue_s(0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j % FA_STAGES;
-        const int valid = min(FA_BN, S - j * FA_BN);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t bV = smem_u32(sV + st * FA_KV_BYTES);
-        const int nk = (valid + 15) / 16;    // chunks of 16 keys that hold a key
+      }
+      __syncwarp();
+    };
+    while (loaded < FA_STAGES && loaded < n_blocks) load_next();
+    issue_s(0);
+    for (int j = 0; j < n_blocks; ++j) {
+      const int st = j % FA_STAGES;
+      const int nk = (min(FA_BN, S - j * FA_BN) + 15) / 16;    // chunks of 16 keys that hold a key
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (lane == 0 && j < 5) stamp(40 + 2 * j);
+      const uint64_t dV = dV0 + static_cast<uint64_t>(st * (FA_KV_BYTES >> 4));
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k)
           if (k < nk)
-            umma_f16_ts(tmem_base + FA_TMEM_O, tmem_base + 8 * k, make_sdesc_sw128(bV + k * 2048, 8192, 1024), IDESC_O,
-                        (j > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ts(tmem_u + FA_TMEM_O, tmem_u + 8 * k, dV + (2048 >> 4) * k, IDESC_O, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
-        // S_{j+1} follows P V_j in issue order: the tensor pipe executes in order, so it cannot overwrite P_j early
-        if (j + 1 < n_blocks) issue_s(j + 1);
-        // refill the slot P V_j is draining (a short wait: that MMA is already running)
-        if (loaded < n_blocks) load_next();
       }
+      __syncwarp();
+      // S_{j+1} follows P V_j in issue order: the tensor pipe executes in order, so it cannot overwrite P_j early
+      if (j + 1 < n_blocks) issue_s(j + 1);
+      if (lane == 0 && j < 5) stamp(41 + 2 * j);
+      // refill the slot P V_j is draining (a short wait: that MMA is already running)
+      if (loaded < n_blocks) load_next();
     }
     __syncwarp();
   } else {
@@ -299,7 +319,8 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 
   if (threadIdx.x == 64) stamp(31);
-  if (dbg != nullptr && threadIdx.x == 64) {   // development only: per-CTA [start, end, sm] after the 64 phase stamps
+#ifdef OWL_FA_TIMELINE
+  if (dbg != nullptr && threadIdx.x == 64) {   // per-CTA [start, end, sm] after the 64 phase stamps
     const long long cta = blockIdx.x + gridDim.x * (blockIdx.y + 1LL * gridDim.y * blockIdx.z);
     long long t;
     uint32_t sm;
@@ -308,6 +329,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     dbg[64 + 3 * cta + 1] = t;
     dbg[64 + 3 * cta + 2] = sm;
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

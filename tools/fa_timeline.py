@@ -1,3 +1,5 @@
+"""Phase timeline of the fused attention kernel (dev tool).  Needs the instrumented build:
+    make -C owl_vit_object_detection_b200/csrc clean && make -C owl_vit_object_detection_b200/csrc -j8 FA_TIMELINE=1"""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,7 +21,9 @@ t0 = t[0]
 names = {0: "setup done", 1: "after pdl wait", 30: "PV last done", 31: "epilogue stored"}
 for j in range(5):
     names[2 + 4 * j] = f"S{j} ready"; names[3 + 4 * j] = f"max{j} known"; names[4 + 4 * j] = f"P{j} written"; names[5 + 4 * j] = f"p_full{j} arrived"
-for k in sorted(names):
+for j in range(5):
+    names[40 + 2 * j] = f"  ctl: p_full{j} seen"; names[41 + 2 * j] = f"  ctl: PV{j}+S{j+1} issued"
+for k in sorted(names, key=lambda k: t[k]):
     if t[k]: print(f"{names[k]:18s} +{(t[k] - t0) / 1000:.2f} us")
 
 import numpy as np
