@@ -17,7 +17,7 @@ def _ref(qkv, B, S, H, dh):
 
 
 @pytest.mark.parametrize("B,S,H", [(2, 577, 12), (1, 17, 2), (3, 208, 1), (1, 209, 2), (2, 416, 3), (1, 625, 2),
-                                    (1, 1300, 2)])
+                                    (1, 1300, 2), (2, 65, 2), (1, 129, 3), (1, 64, 1), (1, 1, 1), (1, 3601, 1)])
 def test_flash_attn_fwd(B, S, H):
     from owl_vit_object_detection_b200 import ops
     dh = 64
