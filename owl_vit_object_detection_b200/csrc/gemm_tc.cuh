@@ -559,7 +559,7 @@ struct EpiF32 {
     float alpha;
     const float* alpha_dev;
   };
-  struct Pre { float4 bias; float4 add[8]; };
+  struct Pre { float4 bias; float4 add[8]; float4 b4; };
   // line phase gather of resid + pos + old output for the 32 x 32 tile at column n (registers only).
   // All loads of a chunk are issued back to back BEFORE anything consumes them: the SM issues in order, so a
   // consumer (or a data-dependent branch) between two loads would expose one full memory latency per load
@@ -636,9 +636,50 @@ struct EpiF32 {
   static __device__ __forceinline__ bool has_addend(const Params& p) {
     return p.resid != nullptr || p.pos != nullptr || p.mode == 1;
   }
+  // Lean path (the layer GEMMs): aligned rows, plain row mapping, store or accumulate, every column chunk of the
+  // warp's slice fully inside the matrix.  Bias and addend are then applied in the LINE phase, where a lane owns
+  // four fixed columns of eight rows: the bias is one float4 per chunk (no shuffles), the addend never goes through
+  // shared memory, and a store costs a handful of instructions.  The generic path below spends ~85 instructions per
+  // 16-byte store on its bounds / mode / row-remap handling, which with two epilogue warps per scheduler is pure
+  // exposed latency (measured: 5.3 us per 128 x 192 tile without any global traffic).
+  template <int BN>
+  static __device__ __forceinline__ bool lean(const Params& p, int n0, int N) {
+    return p.vec_ok != 0 && p.mode != 2 && p.rows_per_img == 0 && p.pos == nullptr && n0 + BN <= N &&
+           (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  }
+  // line-phase operands of the 32 x 32 chunk at column n: addend rows (clamped to M - 1) and the bias float4
+  static __device__ __forceinline__ void lean_fetch(const Params& p, const float* out, int row0, int n, int M, int lane,
+                                                    float4* add, float4& b4) {
+    const int sr = lane >> 3, col = n + (lane & 7) * 4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.resid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        add[i] = *reinterpret_cast<const float4*>(p.resid + (long long)min(row0 + i * 4 + sr, M - 1) * p.ldr + col);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) add[i] = z;
+    }
+    if (p.mode == 1) {
+      float4 r1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        r1[i] = *reinterpret_cast<const float4*>(out + (long long)min(row0 + i * 4 + sr, M - 1) * p.ldo + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { add[i].x += r1[i].x; add[i].y += r1[i].y; add[i].z += r1[i].z; add[i].w += r1[i].w; }
+    }
+    b4 = p.bias ? ldg_f4(p.bias + col) : z;
+  }
   template <int BN>
   static __device__ __forceinline__ void prologue(const Params& p, Pre& pre, int g, int row0, int lane, int n0, int M,
                                                   int N) {
+    if (lean<BN>(p, n0, N)) {
+      if (row0 < M) {
+        const int outer = g / p.H, head = g - outer * p.H;
+        lean_fetch(p, p.out + outer * p.o_sb + head * p.o_sh, row0, n0, M, lane, pre.add, pre.b4);
+      }
+      return;
+    }
     pre.bias = load_bias_slice<BN>(p.bias, n0, N, lane);
     if (has_addend(p) && row0 < M && n0 < N) {
       const int outer = g / p.H, head = g - outer * p.H;
@@ -656,6 +697,46 @@ struct EpiF32 {
     if (!has_k && p.mode != 0) return;  // an empty K slice adds nothing
     const bool has_add = has_addend(p);
     const int sr = lane >> 3, sc = lane & 7;
+    if (lean<BN>(p, n0, N)) {
+      float* d0 = out + (long long)(row0 + sr) * p.ldo + n0 + sc * 4;
+      const long long step = 4LL * p.ldo;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        // next chunk's line-phase operands: in flight behind this chunk's work
+        float4 nadd[8], nb4;
+        if (c + 1 < BN / 32) lean_fetch(p, out, row0, n0 + (c + 1) * 32, M, lane, nadd, nb4);
+        // row phase: accumulator -> staging (thread t owns row t)
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a0 = has_k ? __uint_as_float(r[4 * q]) * alpha : 0.f, a1 = has_k ? __uint_as_float(r[4 * q + 1]) * alpha : 0.f;
+          const float a2 = has_k ? __uint_as_float(r[4 * q + 2]) * alpha : 0.f, a3 = has_k ? __uint_as_float(r[4 * q + 3]) * alpha : 0.f;
+          sts128(stage_addr(stage, lane, q), make_uint4(__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3)));
+        }
+        __syncwarp();
+        // line phase: + bias + addend, whole 128-byte lines out
+        float* d = d0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 u = lds128(stage_addr(stage, i * 4 + sr, sc));
+          float4 o;
+          o.x = __uint_as_float(u.x) + pre.b4.x + pre.add[i].x;
+          o.y = __uint_as_float(u.y) + pre.b4.y + pre.add[i].y;
+          o.z = __uint_as_float(u.z) + pre.b4.z + pre.add[i].z;
+          o.w = __uint_as_float(u.w) + pre.b4.w + pre.add[i].w;
+          if (row0 + i * 4 + sr < M) *reinterpret_cast<float4*>(d + i * step) = o;
+        }
+        __syncwarp();
+        if (c + 1 < BN / 32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pre.add[i] = nadd[i];
+          pre.b4 = nb4;
+        }
+      }
+      return;
+    }
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int n = n0 + c * 32;
