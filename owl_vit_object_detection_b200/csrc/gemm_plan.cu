@@ -142,6 +142,7 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   const long long ctiles = mbc * ((a.N + p.bn - 1) / p.bn) * G * a.split_k;   // cluster tiles
   const long long max_clusters = num_sms() / p.cm;
   p.grid = static_cast<int>((ctiles < max_clusters ? ctiles : max_clusters) * p.cm);
+  p.tiles = ctiles;
   return OWL_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.h"
 #include "gemm_tc.cuh"
+#include <algorithm>
 
 namespace owl {
 
@@ -17,6 +18,7 @@ struct GemmPlan {
   EpiF32::Params p32;
   EpiPool3::Params pp;
   int grid;
+  long long tiles;   // cluster tiles of the whole problem
 };
 
 // `bn` = 0 lets the planner choose the N tile.
@@ -28,15 +30,17 @@ int gemm_launch_kk(const GemmPlan& p, cudaStream_t s);
 int gemm_launch_kmn(const GemmPlan& p, cudaStream_t s);
 int gemm_launch_mnmn(const GemmPlan& p, cudaStream_t s);
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1, int MINB = 1>
 int gemm_launch_one(const GemmPlan& p, const typename Epi::Params& ep, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CM>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CM, MINB>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN / CM)));
+    OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN / CM, MINB)));
     configured = true;
   }
-  OWL_CUDA(launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), gemm_smem_bytes(BN / CM), s, CM, p.tmA, p.tmB, p.gs, ep));
+  // persistent grid: one CTA per SM slot the flavour is built for
+  const int grid = MINB == 1 ? p.grid : static_cast<int>(std::min<long long>(p.tiles, 1LL * MINB * num_sms()));
+  OWL_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(BN / CM, MINB), s, CM, p.tmA, p.tmB, p.gs, ep));
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

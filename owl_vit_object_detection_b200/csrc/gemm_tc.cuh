@@ -39,13 +39,17 @@ struct GemmShape {
 };
 
 __host__ __device__ constexpr int gemm_stage_bytes(int BN) { return (GEMM_BM + BN) * GEMM_BK * 2; }
-__host__ __device__ constexpr int gemm_num_stages(int BN) {
-  return GEMM_SMEM_BUDGET / gemm_stage_bytes(BN) > 8 ? 8 : GEMM_SMEM_BUDGET / gemm_stage_bytes(BN);
+// MINB = CTAs per SM the kernel is built for.  2 is the flavour for short-K, epilogue-dominated problems (the
+// attention-backward GEMMs, K = 64: one k-block per tile): a 64 KB operand ring and <= 102 registers let two CTAs
+// share an SM, i.e. sixteen epilogue warps instead of eight hide each other's latencies.
+__host__ __device__ constexpr int gemm_num_stages(int BN, int MINB = 1) {
+  const int budget = MINB == 2 ? 64 * 1024 : GEMM_SMEM_BUDGET;
+  return budget / gemm_stage_bytes(BN) > 8 ? 8 : budget / gemm_stage_bytes(BN);
 }
 constexpr int GEMM_EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B transposition buffer
 // BN here is the number of B rows ONE CTA stages (BN / 2 in the pair flavour)
-__host__ __device__ constexpr int gemm_smem_bytes(int BN) {
-  return gemm_num_stages(BN) * gemm_stage_bytes(BN) + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ +
+__host__ __device__ constexpr int gemm_smem_bytes(int BN, int MINB = 1) {
+  return gemm_num_stages(BN, MINB) * gemm_stage_bytes(BN) + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ +
          256 /*barriers*/;
 }
 __host__ __device__ constexpr int gemm_tmem_cols(int BN) {
@@ -75,8 +79,8 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int k16) {
 //   empty_bar  per CTA, count 1: the leader's tcgen05.commit is multicast to both CTAs
 //   tfull_bar  per CTA, count 1: same multicast commit after the last k-block of a tile
 //   tempty_bar leader only, count 2 x epilogue warps: the peer's epilogue warps arrive remotely
-template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1, int MINB = 1>
+__global__ void __launch_bounds__(GEMM_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmShape gs, const typename Epi::Params ep) {
   static_assert(CM == 1 || CM == 2, "1 = single CTA, 2 = CTA pair (cta_group::2)");
@@ -86,7 +90,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int BN_CTA = BN / CM;                       // B rows held by one CTA
   constexpr int B_BYTES = BN_CTA * GEMM_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = gemm_num_stages(BN_CTA);
+  constexpr int STAGES = gemm_num_stages(BN_CTA, MINB);
+  static_assert(MINB == 1 || (CM == 1 && 2 * gemm_tmem_cols(BN) <= 512), "two CTAs per SM: both accumulators must fit TMEM");
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN);
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(!B_MN || BN % 64 == 0, "MN-major B tiles are loaded in 64-wide chunks");
