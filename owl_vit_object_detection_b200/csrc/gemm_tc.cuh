@@ -649,7 +649,7 @@ struct EpiF32 {
   // exposed latency (measured: 5.3 us per 128 x 192 tile without any global traffic).
   template <int BN>
   static __device__ __forceinline__ bool lean(const Params& p, int n0, int N) {
-    return p.vec_ok != 0 && p.mode != 2 && p.rows_per_img == 0 && p.pos == nullptr && n0 + BN <= N &&
+    return p.vec_ok != 0 && p.rows_per_img == 0 && p.pos == nullptr && n0 + BN <= N &&
            (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
   }
   // line-phase operands of the 32 x 32 chunk at column n: addend rows (clamped to M - 1) and the bias float4
@@ -731,7 +731,10 @@ struct EpiF32 {
           o.y = __uint_as_float(u.y) + pre.b4.y + pre.add[i].y;
           o.z = __uint_as_float(u.z) + pre.b4.z + pre.add[i].z;
           o.w = __uint_as_float(u.w) + pre.b4.w + pre.add[i].w;
-          if (row0 + i * 4 + sr < M) *reinterpret_cast<float4*>(d + i * step) = o;
+          if (row0 + i * 4 + sr < M) {
+            if (p.mode == 2) atomicAdd(reinterpret_cast<float4*>(d + i * step), o);   // split-K / shared outputs: one 16-byte red
+            else *reinterpret_cast<float4*>(d + i * step) = o;
+          }
         }
         __syncwarp();
         if (c + 1 < BN / 32) {
