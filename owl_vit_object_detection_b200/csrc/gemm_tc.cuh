@@ -499,12 +499,29 @@ struct EpiF16 {
           uint32_t r[32];
           tmem_ld32(taddr + c * 64 + h * 32, r);
           tmem_ld_wait();
+          // The epilogue is a serial chain on two warps per scheduler: every instruction here is exposed latency.
+          // (has_k is always true for this epilogue: split-K needs the fp32 atomic one.)
           float v[32];
+          if (alpha == 1.0f) {      // warp-uniform
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * alpha : 0.0f;
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+          }
           if (p.bias) {
+            if (n + h * 32 + 32 <= N) {
+              // all lanes read the same eight 16-byte words: one broadcast transaction each (no shuffles)
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n + h * 32);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) add_bias4(v + 4 * q, pre.bias, c * 16 + h * 8 + q);
+              for (int q = 0; q < 8; ++q) {
+                const float4 bq = __ldg(b4 + q);
+                v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) add_bias4(v + 4 * q, pre.bias, c * 16 + h * 8 + q);
+            }
           }
           if constexpr (kRowVec) {
 #pragma unroll
