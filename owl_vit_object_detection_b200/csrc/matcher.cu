@@ -187,6 +187,13 @@ __device__ __forceinline__ Cand cand_combine(const Cand& a, const Cand& b) {
 
 constexpr int LSAP_WARPS = 4;
 
+// bytes of the solver's own state in the CTA-per-image kernel (the staged cost rows follow, 16-byte aligned)
+__host__ __device__ inline size_t lsap_block_base_bytes(int P, int Tmax) {
+  const int Tpad = (Tmax + 4) & ~3;
+  const size_t b = sizeof(double) * (2 * (size_t)P + Tpad) + sizeof(short) * (3 * (size_t)P + 3 * Tpad + 8);
+  return (b + 15) & ~size_t(15);
+}
+
 __global__ void __launch_bounds__(LSAP_WARPS * 32)
 lsap_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets, int B, int P, int Tmax,
             int* __restrict__ match_pred /*[B,Tmax]*/, int* __restrict__ status) {
@@ -296,7 +303,7 @@ lsap_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets
 template <int NT>
 __global__ void __launch_bounds__(NT)
 lsap_block_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets, int P, int Tmax,
-                  int* __restrict__ match_pred /*[B,Tmax]*/, int* __restrict__ status) {
+                  int* __restrict__ match_pred /*[B,Tmax]*/, int* __restrict__ status, int smem_rows) {
   pdl_grid_wait();
   extern __shared__ __align__(16) unsigned char lsm[];
   constexpr int NW = NT / 32;
@@ -314,9 +321,20 @@ lsap_block_kernel(const float* __restrict__ costT, const int* __restrict__ num_t
   short* col4row = remaining + P;
   short* sr_list = col4row + Tpad;
   short* sc_list = sr_list + Tpad + 4;
+  // the image's cost rows, staged once: every scan below would otherwise start with an exposed global-load
+  // latency (~2 scans per target, 0.6 us each).  Rows that do not fit (smem_rows) are read from global memory.
+  float* scost = reinterpret_cast<float*>(lsm + lsap_block_base_bytes(P, Tmax));
 
   const int nr = num_targets[b], nc = P;
   const float* cost = costT + 1LL * b * Tmax * P;
+  const int rows_s = min(nr, smem_rows);
+  if ((P & 3) == 0) {
+    const float4* src = reinterpret_cast<const float4*>(cost);
+    float4* dst = reinterpret_cast<float4*>(scost);
+    for (int k = tid; k < rows_s * (P >> 2); k += NT) dst[k] = __ldg(src + k);
+  } else {
+    for (int k = tid; k < rows_s * P; k += NT) scost[k] = __ldg(cost + k);
+  }
   for (int j = tid; j < nc; j += NT) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
   for (int i = tid; i < nr; i += NT) { u[i] = 0.0; col4row[i] = -1; }
   __syncthreads();
@@ -331,11 +349,13 @@ lsap_block_kernel(const float* __restrict__ costT, const int* __restrict__ num_t
       if (tid == 0) sr_list[n_sr] = static_cast<short>(i);
       ++n_sr;
       const double ui = u[i];
-      const float* crow = cost + 1LL * i * nc;
+      const bool in_smem = i < rows_s;   // block-uniform
+      const float* crow = in_smem ? scost + i * nc : cost + 1LL * i * nc;
       Cand best = {0.0, 0, -1};
       for (int it = tid; it < num_remaining; it += NT) {
         const int j = remaining[it];
-        const double r = ((min_val + static_cast<double>(__ldg(crow + j))) - ui) - v[j];
+        const float cij = in_smem ? crow[j] : __ldg(crow + j);
+        const double r = ((min_val + static_cast<double>(cij)) - ui) - v[j];
         double sj = spc[j];
         if (r < sj) { path[j] = static_cast<short>(i); spc[j] = r; sj = r; }
         const Cand c = {sj, row4col[j] == -1 ? 1 : 0, it};
@@ -720,8 +740,10 @@ extern "C" int owl_lsap(const float* costT, const int* num_targets, int B, int P
   if (B <= 2 * num_sms()) {
     // few images: one CTA per image so that the slowest image finishes sooner
     constexpr int NT = 256;
-    const size_t smem1 = lsap_smem_per_warp(P, Tmax);
-    OWL_CHECK_ARG(smem1 <= 227 * 1024, "lsap: P = %d needs %zu bytes of shared memory", P, smem1);
+    const size_t base1 = lsap_block_base_bytes(P, Tmax);
+    OWL_CHECK_ARG(base1 <= 200 * 1024, "lsap: P = %d needs %zu bytes of shared memory", P, base1);
+    const int smem_rows = static_cast<int>(std::min<size_t>(Tmax, (200 * 1024 - base1) / (sizeof(float) * P)));
+    const size_t smem1 = base1 + sizeof(float) * P * smem_rows;
     static size_t configured1 = 48 * 1024;
     if (smem1 > configured1) {
       OWL_CUDA(cudaFuncSetAttribute(lsap_block_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -729,7 +751,7 @@ extern "C" int owl_lsap(const float* costT, const int* num_targets, int B, int P
       configured1 = smem1;
     }
     OWL_LAUNCH(lsap_block_kernel<NT>, B, NT, smem1, static_cast<cudaStream_t>(stream), costT, num_targets, P, Tmax,
-                                                                               match_pred, status);
+                                                                               match_pred, status, smem_rows);
     OWL_CUDA(cudaGetLastError());
     return OWL_OK;
   }
