@@ -52,9 +52,14 @@ __device__ __forceinline__ float giou_pair(const Box& a, const Box& b) {
 //   phase 2: lane = prediction, warp strides over targets: C = (L1 + (-p[label])) + (-GIoU); 128-byte
 //            coalesced stores into costT[b][t][p0 .. p0+31].
 // =====================================================================================================
-constexpr int COST_ROWS = 32;
+constexpr int COST_ROWS = 64;      // predictions per CTA (two passes of 32 rows x 8 lanes through the softmax)
 constexpr int COST_THREADS = 256;
 
+// The kernel is instruction-issue bound (ncu: issue slots 73 % busy, DRAM 21 %: the index-exact arithmetic costs
+// ~4x a fast-math version), so the row length is a template parameter (no dead iterations / predicates) and a CTA
+// covers 64 predictions (the per-CTA target set-up is amortised, and 2 x T (row group, target) items fill the
+// eight warps of the pair phase better than T items do).
+template <int NVEC /* float4 per lane: ceil(C / 32) */, bool VEC /* C % 4 == 0 */>
 __global__ void __launch_bounds__(COST_THREADS)
 matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ boxes,
                     const long long* __restrict__ labels, const float* __restrict__ tboxes,
@@ -62,8 +67,8 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
                     int* __restrict__ status) {
   pdl_grid_wait();
   extern __shared__ float sm[];
-  float* prob = sm;                                   // [32][C + 1]
-  float* pbox = prob + COST_ROWS * (C + 1);           // [32][4]
+  float* prob = sm;                                   // [64][C + 1]
+  float* pbox = prob + COST_ROWS * (C + 1);           // [64][4]
   float* tbox = pbox + COST_ROWS * 4;                 // [Tmax][4]
   int* tlab = reinterpret_cast<int*>(tbox + Tmax * 4);  // [Tmax]
 
@@ -74,30 +79,28 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
 
   for (int i = threadIdx.x; i < T * 4; i += COST_THREADS) tbox[i] = tboxes[(1LL * b * Tmax) * 4 + i];
   for (int i = threadIdx.x; i < T; i += COST_THREADS) tlab[i] = static_cast<int>(labels[1LL * b * Tmax + i]);
-  for (int i = threadIdx.x; i < COST_ROWS * 4; i += COST_THREADS) {
+  {
+    const int i = threadIdx.x;                       // 64 rows x 4 coordinates = 256 threads
     const int p = p0 + (i >> 2);
     pbox[i] = p < P ? boxes[(1LL * b * P + p) * 4 + (i & 3)] : 0.0f;
   }
   // phase 1: softmax(sims[b, p, :])  (reference src/matcher.py:106-108).  Eight lanes per row, four rows per warp,
-  // so the CTA's 32 rows are in flight at once: every lane issues all of its 128-bit loads before the first
-  // reduction (rows are 4 * C bytes apart, a warp access covers four rows).  Falls back to scalar loads when C is
-  // not a multiple of 4.
+  // 32 rows per pass: every lane issues all of its 128-bit loads (of BOTH passes) before the first reduction.
   {
-    const int r = warp * 4 + (lane >> 3), sub = lane & 7;
-    const int p = p0 + r;
-    const bool row_ok = p < P;
-    const float* row = sims + (1LL * b * P + (row_ok ? p : 0)) * C;
-    constexpr int MAXV = 8;                       // up to 8 * 32 = 256 classes per row
-    const int nvec = (C + 31) / 32;               // float4 per lane
-    float4 v[MAXV];
-    const bool vec = (C & 3) == 0;
+    const int sub = lane & 7;
+    float4 v[2][NVEC];
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (k < nvec) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 32 + warp * 4 + (lane >> 3);
+      const int p = p0 + r;
+      const bool row_ok = p < P;
+      const float* row = sims + (1LL * b * P + (row_ok ? p : 0)) * C;
+#pragma unroll
+      for (int k = 0; k < NVEC; ++k) {
         const int c = k * 32 + sub * 4;
         float4 t = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
         if (row_ok && c < C) {
-          if (vec) {
+          if (VEC) {
             t = __ldg(reinterpret_cast<const float4*>(row + c));
           } else {
             t.x = row[c];
@@ -106,39 +109,41 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
             if (c + 3 < C) t.w = row[c + 3];
           }
         }
-        v[k] = t;
+        v[pass][k] = t;
       }
     }
-    float m = -CUDART_INF_F;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k)
-      if (k < nvec) m = fmaxf(m, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 32 + warp * 4 + (lane >> 3);
+      float m = -CUDART_INF_F;
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float s = 0.f;
+      for (int k = 0; k < NVEC; ++k)
+        m = fmaxf(m, fmaxf(fmaxf(v[pass][k].x, v[pass][k].y), fmaxf(v[pass][k].z, v[pass][k].w)));
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (k < nvec) {
+      for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NVEC; ++k) {
         const int c = k * 32 + sub * 4;
-        v[k].x = c < C ? expf(fsub(v[k].x, m)) : 0.f;
-        v[k].y = c + 1 < C ? expf(fsub(v[k].y, m)) : 0.f;
-        v[k].z = c + 2 < C ? expf(fsub(v[k].z, m)) : 0.f;
-        v[k].w = c + 3 < C ? expf(fsub(v[k].w, m)) : 0.f;
-        s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        float4& x = v[pass][k];
+        x.x = c < C ? expf(fsub(x.x, m)) : 0.f;
+        x.y = c + 1 < C ? expf(fsub(x.y, m)) : 0.f;
+        x.z = c + 2 < C ? expf(fsub(x.z, m)) : 0.f;
+        x.w = c + 3 < C ? expf(fsub(x.w, m)) : 0.f;
+        s += (x.x + x.y) + (x.z + x.w);
       }
-    }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float inv = fdiv(1.0f, s);
+      for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float inv = fdiv(1.0f, s);
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (k < nvec) {
+      for (int k = 0; k < NVEC; ++k) {
         const int c = k * 32 + sub * 4;
         float* dst = prob + r * (C + 1) + c;
-        if (c < C) dst[0] = fmul(v[k].x, inv);
-        if (c + 1 < C) dst[1] = fmul(v[k].y, inv);
-        if (c + 2 < C) dst[2] = fmul(v[k].z, inv);
-        if (c + 3 < C) dst[3] = fmul(v[k].w, inv);
+        const float4 x = v[pass][k];
+        if (c < C) dst[0] = fmul(x.x, inv);
+        if (c + 1 < C) dst[1] = fmul(x.y, inv);
+        if (c + 2 < C) dst[2] = fmul(x.z, inv);
+        if (c + 3 < C) dst[3] = fmul(x.w, inv);
       }
     }
   }
@@ -151,16 +156,17 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
   for (int i = threadIdx.x; i < T; i += COST_THREADS)
     if (!(tbox[i * 4 + 2] >= tbox[i * 4 + 0]) || !(tbox[i * 4 + 3] >= tbox[i * 4 + 1])) atomicOr(status, 1);
 
-  // phase 2
-  const int p = p0 + lane;
-  if (p < P) {
-    const Box pb = {pbox[lane * 4 + 0], pbox[lane * 4 + 1], pbox[lane * 4 + 2], pbox[lane * 4 + 3]};
-    for (int t = warp; t < T; t += COST_THREADS / 32) {
+  // phase 2: items = (row group of 32 predictions, target); lane = prediction inside the group
+  for (int item = warp; item < 2 * T; item += COST_THREADS / 32) {
+    const int grp = item & 1, t = item >> 1;
+    const int row = grp * 32 + lane, p = p0 + row;
+    if (p < P) {
+      const Box pb = {pbox[row * 4 + 0], pbox[row * 4 + 1], pbox[row * 4 + 2], pbox[row * 4 + 3]};
       const Box tb = {tbox[t * 4 + 0], tbox[t * 4 + 1], tbox[t * 4 + 2], tbox[t * 4 + 3]};
       // torch.cdist(p=1): ((|dx0| + |dy0|) + |dx1|) + |dy1|   (reference src/matcher.py:121)
       const float l1 = fadd(fadd(fadd(fabsf(fsub(pb.x0, tb.x0)), fabsf(fsub(pb.y0, tb.y0))),
                                  fabsf(fsub(pb.x1, tb.x1))), fabsf(fsub(pb.y1, tb.y1)));
-      const float pr = prob[lane * (C + 1) + tlab[t]];
+      const float pr = prob[row * (C + 1) + tlab[t]];
       const float gi = giou_pair(pb, tb);
       // (cost_bbox + cost_class) + cost_giou with cost_class = -p, cost_giou = -giou (src/matcher.py:127-131)
       costT[(1LL * b * Tmax + t) * P + p] = fsub(fsub(l1, pr), gi);
@@ -717,10 +723,30 @@ extern "C" int owl_matcher_cost(const float* sims, const float* boxes, const lon
   OWL_CHECK_ARG(B > 0 && P > 0 && C > 0 && Tmax > 0, "matcher_cost: empty dimension");
   OWL_CHECK_ARG(C <= 256, "matcher_cost: C = %d classes is more than the 256 this kernel keeps in registers", C);
   const size_t smem = sizeof(float) * (COST_ROWS * (C + 1) + COST_ROWS * 4 + Tmax * 4) + sizeof(int) * Tmax;
-  OWL_CHECK_ARG(smem <= 48 * 1024, "matcher_cost: C = %d / Tmax = %d need %zu bytes of shared memory", C, Tmax, smem);
+  OWL_CHECK_ARG(smem <= 100 * 1024, "matcher_cost: C = %d / Tmax = %d need %zu bytes of shared memory", C, Tmax, smem);
   dim3 grid((P + COST_ROWS - 1) / COST_ROWS, B);
-  OWL_LAUNCH(matcher_cost_kernel, grid, COST_THREADS, smem, static_cast<cudaStream_t>(stream), 
-      sims, boxes, labels, tboxes, num_targets, costT, P, C, Tmax, status);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nvec = (C + 31) / 32;
+  const bool vec = (C & 3) == 0;
+#define OWL_COST_CASE(NV)                                                                                           \
+  case NV:                                                                                                          \
+    if (vec) {                                                                                                      \
+      static bool cfg = false;                                                                                      \
+      if (!cfg) { OWL_CUDA(cudaFuncSetAttribute(matcher_cost_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; } \
+      OWL_LAUNCH((matcher_cost_kernel<NV, true>), grid, COST_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, \
+                 costT, P, C, Tmax, status);                                                                        \
+    } else {                                                                                                        \
+      static bool cfg = false;                                                                                      \
+      if (!cfg) { OWL_CUDA(cudaFuncSetAttribute(matcher_cost_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; } \
+      OWL_LAUNCH((matcher_cost_kernel<NV, false>), grid, COST_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, \
+                 costT, P, C, Tmax, status);                                                                        \
+    }                                                                                                               \
+    break;
+  switch (nvec) {
+    OWL_COST_CASE(1) OWL_COST_CASE(2) OWL_COST_CASE(3) OWL_COST_CASE(4) OWL_COST_CASE(5) OWL_COST_CASE(6) OWL_COST_CASE(7)
+    OWL_COST_CASE(8)
+  }
+#undef OWL_COST_CASE
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }
