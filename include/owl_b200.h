@@ -116,6 +116,12 @@ int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse, int B, in
  * (= alpha * sum_j P dP), consumed by owl_gemm act 6. */
 int owl_attn_delta(const void* ctx_f16, const void* dctx_f16, float* delta, int B, int S, int H, int head_dim,
                    float alpha, void* stream);
+/* Fused attention backward (autograd of HF:393-404), head_dim 64: from the packed qkv [B*S, 3*H*64], dctx [B*S, H*64],
+ * the forward's lse [B][H][S] and delta [B][H][S] (= scale * rowsum(dctx . ctx), owl_attn_delta) to dqkv [B*S, 3*H*64]
+ * (fp16, same packing as qkv).  Scores, probabilities and their gradients stay in TMEM / shared memory; dq32
+ * [B*S, H*64] fp32 is scratch (the per-key-block dQ contributions are accumulated there with 16-byte atomics). */
+int owl_attn_bwd(const void* qkv_f16, const void* dctx_f16, const float* lse, const float* delta, void* dqkv_f16,
+                 float* dq32, int B, int S, int H, int head_dim, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Image preprocessing (reference src/dataset.py:64-71 -> HF OwlViTImageProcessor of the pinned transformers 4.30.2:

@@ -14,7 +14,7 @@ Data layout in HBM (B images, S = P + 1 tokens, D hidden):
   residual stream   x      fp32 [B*S, D]   (row = image-major token index, CLS first)
   GEMM operands     *16    fp16, row-major, produced by the LayerNorm / previous GEMM epilogue
   QKV               qkv16  fp16 [B*S, 3D]  (q | k | v column blocks, head h at columns h*dh inside a block)
-  attention probs   fp16 [B*H, S, Sp]      (backward only, recomputed; Sp = S rounded up to 8: 16-byte rows for TMA)
+  attention scores / probabilities never leave the SM (fused forward and backward kernels)
 """
 from __future__ import annotations
 
@@ -115,9 +115,8 @@ class Workspace:
             b.dmpre = z((B * S, F), f16)
             b.dh32 = z((B * S, D), f32)
             b.dctx = z((B * S, D), f16)
-            b.probs = z((B * H, S, self.Sp), f16)      # recomputed from q, k and the saved log-sum-exp
-            b.dprobs = z((B * H, S, self.Sp), f16)
             b.delta = z((B * H, S), f32)
+            b.dq32 = z((B * S, D), f32)                # fp32 accumulation of dQ across key blocks
             b.dqkv = z((B * S, 3 * D), f16)
             self._bw = b
         return self._bw
@@ -338,31 +337,10 @@ class Engine:
         ops.gemm(bw.g16, self.p16(p + "self_attn.out_proj.weight"), bw.dctx, M=M, N=D, K=D, b_mn=True)
         qkv, dqkv = ws.qkv, bw.dqkv
         scale = dh ** -0.5
-        # P = exp(scale q k^T - lse): the probabilities of HF:398, recomputed in the GEMM epilogue
-        ops.gemm(qkv, qkv[:, D:], bw.probs, M=S, N=S, K=dh, a_ld=3 * D, b_ld=3 * D, ldo=Sp,
-                 batches_outer=B, heads=H, a_outer_stride=S * 3 * D, b_outer_stride=S * 3 * D,
-                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp,
-                 alpha=scale, act="exp_row", rowvec=ws.lse, rowvec_stride=S)
-        # dV = P^T dctx
-        ops.gemm(bw.probs, bw.dctx, dqkv[:, 2 * D:], M=S, N=dh, K=S, a_mn=True, b_mn=True, a_ld=Sp, b_ld=D, ldo=3 * D,
-                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
-                 b_outer_stride=S * D, b_head_col=dh, o_outer_stride=S * 3 * D, o_head_stride=dh)
-        # dS = P * (dctx V^T - sum_j P dP) * scale, the softmax backward fused into the dP GEMM's epilogue;
-        # sum_j P_ij dP_ij = sum_d dctx_id ctx_id (row term computed from the [B*S, D] tensors)
+        # attention backward (autograd of HF:393-404) in one kernel: P is recomputed from the saved log-sum-exp,
+        # dS = P (scale dctx v^T - delta) with delta = scale * rowsum(dctx . ctx); S / P / dP / dS stay on the SM
         ops.attn_delta(ws.ctx, bw.dctx, bw.delta, B=B, S=S, H=H, head_dim=dh, alpha=scale)
-        ops.gemm(bw.dctx, qkv[:, 2 * D:], bw.dprobs, M=S, N=S, K=dh, a_ld=D, b_ld=3 * D, ldo=Sp,
-                 batches_outer=B, heads=H, a_outer_stride=S * D, b_outer_stride=S * 3 * D,
-                 a_head_col=dh, b_head_col=dh, o_outer_stride=H * S * Sp, o_head_stride=S * Sp,
-                 alpha=scale, act="softmax_grad", act_src=bw.probs, act_src_outer_stride=H * S * Sp,
-                 act_src_head_stride=S * Sp, rowvec=bw.delta, rowvec_stride=S)
-        # dQ = dS K
-        ops.gemm(bw.dprobs, qkv[:, D:], dqkv, M=S, N=dh, K=S, b_mn=True, a_ld=Sp, b_ld=3 * D, ldo=3 * D,
-                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
-                 b_outer_stride=S * 3 * D, b_head_col=dh, o_outer_stride=S * 3 * D, o_head_stride=dh)
-        # dK = dS^T Q
-        ops.gemm(bw.dprobs, qkv, dqkv[:, D:], M=S, N=dh, K=S, a_mn=True, b_mn=True, a_ld=Sp, b_ld=3 * D, ldo=3 * D,
-                 batches_outer=B, heads=H, a_outer_stride=H * S * Sp, a_head_stride=S * Sp,
-                 b_outer_stride=S * 3 * D, b_head_col=dh, o_outer_stride=S * 3 * D, o_head_stride=dh)
+        ops.attn_bwd(qkv, bw.dctx, ws.lse, bw.delta, dqkv, bw.dq32, B=B, S=S, H=H, head_dim=dh, scale=scale)
         gw = gspan(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * D, D)
         gb = gspan(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias")
         self._wgrad(dqkv, ws.h1, gw, rows=M, n_out=3 * D, n_in=D, gscale=gs)

@@ -156,6 +156,19 @@ def attn_delta(ctx16: torch.Tensor, dctx16: torch.Tensor, delta: torch.Tensor, *
     return delta
 
 
+def attn_bwd(qkv16: torch.Tensor, dctx16: torch.Tensor, lse: torch.Tensor, delta: torch.Tensor, dqkv16: torch.Tensor,
+             dq32: torch.Tensor, *, B: int, S: int, H: int, head_dim: int, scale: float):
+    """Fused attention backward: dqkv (fp16, packed like qkv) from qkv, dctx, lse and delta; dq32 is fp32 scratch."""
+    assert qkv16.dtype == torch.float16 and dctx16.dtype == torch.float16 and dqkv16.dtype == torch.float16
+    assert qkv16.is_contiguous() and dctx16.is_contiguous() and dqkv16.is_contiguous()
+    _f32(lse), _f32(delta), _f32(dq32)
+    D = H * head_dim
+    assert qkv16.numel() == B * S * 3 * D and dqkv16.numel() == B * S * 3 * D and dq32.numel() == B * S * D
+    check(lib().owl_attn_bwd(_vp(qkv16), _vp(dctx16), _vp(lse), _vp(delta), _vp(dqkv16), _vp(dq32), B, S, H, head_dim,
+                             ctypes.c_float(scale), _sp()), "owl_attn_bwd", kernels=2)
+    return dqkv16
+
+
 def cast_f16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
     _f32(src)
     assert dst.dtype == torch.float16 and dst.numel() == src.numel()

@@ -119,3 +119,35 @@ def test_flash_attn_lse_and_backward_pieces(B, S, H):
     ref_ds = (p64 * (dp - (p64 * dp).sum(-1, keepdim=True)) * scale).reshape(B * H, S, S)
     err = (ds[:, :, :S].double() - ref_ds).abs().max().item()
     assert err <= 1e-2 * ref_ds.abs().max().item(), (err, ref_ds.abs().max().item())
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 577, 12), (1, 209, 2), (1, 128, 1), (2, 300, 3), (1, 65, 1)])
+def test_fused_attention_backward(B, S, H):
+    """owl_attn_bwd (dq, dk, dv in one kernel, scores in TMEM) against fp64 autograd of softmax(q k^T / sqrt(dh)) v.
+    Tolerance: fp16 q/k/v/dctx/P/dS operands, fp32 accumulation -> 1e-2 of each gradient's magnitude."""
+    from owl_vit_object_detection_b200 import ops
+    dh = 64
+    D = H * dh
+    scale = dh ** -0.5
+    g = torch.Generator().manual_seed(7 * S + H)
+    qkv = torch.randn((B * S, 3 * D), generator=g).half().cuda()
+    dctx = torch.randn((B * S, D), generator=g).half().cuda()
+    ctx = torch.zeros((B * S, D), dtype=torch.float16, device="cuda")
+    lse = torch.zeros((B * H, S), dtype=torch.float32, device="cuda")
+    delta = torch.zeros((B * H, S), dtype=torch.float32, device="cuda")
+    ops.flash_attn_fwd(qkv, ctx, B=B, S=S, H=H, head_dim=dh, scale=scale, lse=lse)
+    ops.attn_delta(ctx, dctx, delta, B=B, S=S, H=H, head_dim=dh, alpha=scale)
+    dqkv = torch.full((B * S, 3 * D), float("nan"), dtype=torch.float16, device="cuda")
+    dq32 = torch.empty((B * S, D), dtype=torch.float32, device="cuda")
+    ops.attn_bwd(qkv, dctx, lse, delta, dqkv, dq32, B=B, S=S, H=H, head_dim=dh, scale=scale)
+    torch.cuda.synchronize()
+    x = qkv.double().view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)   # [3, B, H, S, dh]
+    p = torch.softmax(x[0] @ x[1].transpose(-1, -2) * scale, -1)
+    o = (p @ x[2]).permute(0, 2, 1, 3).reshape(B * S, D)
+    o.backward(dctx.double())
+    ref = x.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 3 * D)       # back to the packed layout
+    assert torch.isfinite(dqkv).all()
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        err = (dqkv[:, sl].double() - ref[:, sl]).abs().max().item()
+        mag = ref[:, sl].abs().max().item()
+        assert err <= 1e-2 * mag, (name, err, mag)
