@@ -73,6 +73,11 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -338,6 +343,325 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second generation of the forward kernel.  Same row ownership (one softmax thread per query row, 128 TMEM columns
+// per CTA), but the score block is split into 32-key SUB-BLOCKS that ping-pong between two 32-column TMEM buffers:
+//
+//   TMEM:  S/P buffer 0 @0 (32 cols), S/P buffer 1 @32 (32 cols), O @64 (64 cols);  P_t = 16 packed-fp16 columns
+//          written in place over the first half of its own score buffer
+//   MMA warp:       S_0, S_1;  for t: wait P_t -> O += P_t V_t (2 MMAs, K = 16) -> S_{t+2} = Q K_{t+2}^T (4 MMAs,
+//                   N = 32, into the buffer P_t is being drained from: the tensor pipe executes in order)
+//   softmax thread: for t: wait S_t (issued one whole sub-block ago) -> tcgen05.ld -> max / exp2 / pack ->
+//                   tcgen05.st P_t -> arrive
+//
+// In the first generation every 64-key block was one serial chain  P arrive -> MMA issue -> MMA -> commit -> TMEM
+// load -> exp2 -> TMEM store -> arrive  per CTA (ncu: tensor 23 %, MUFU 43 %, issue 30 % of active cycles: nothing
+// saturated); here the P.V and score MMAs of the neighbouring sub-blocks run under the exponentials, and the
+// 32-score working set per thread leaves room for FOUR CTAs per SM.
+// Template: KV_ROWS = keys per K/V ring slot (32 or 64), STAGES = ring slots, CTAS = CTAs per SM, SPLIT = separate
+// TMA-producer warp (192 threads) instead of one control warp doing both (160 threads).
+constexpr int FA2_SUB = 32;                          // keys per sub-block
+int make_qkv_map(CUtensorMap* out, const void* qkv, int B, int S, int D, uint32_t box_rows);
+
+template <int KV_ROWS, int STAGES, bool SPLIT>
+struct Fa2Cfg {
+  static constexpr int kCtrlWarps = SPLIT ? 2 : 1;
+  static constexpr int kThreads = (kCtrlWarps + 4) * 32;
+  static constexpr int kKvBytes = KV_ROWS * FA_DH * 2;
+  static constexpr int kSmem = FA_Q_BYTES + 2 * STAGES * kKvBytes + 1024 + 256;
+  static constexpr int kSubsPerSlot = KV_ROWS / FA2_SUB;
+};
+
+template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF>
+__global__ void __launch_bounds__((Fa2Cfg<KV_ROWS, STAGES, SPLIT>::kThreads), CTAS)
+flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                       __half* __restrict__ ctx, float* __restrict__ lse, int S, int D, int H, float scale_log2,
+                       long long* __restrict__ prof) {
+  // PROF (dev, OWL_FA_GEN=9x + owl_flash_attn_debug): per-CTA clock64 sums of the loop phases -> prof[cta * 16 + ..]
+  long long pc[6] = {0, 0, 0, 0, 0, 0};
+  long long tk = 0;
+  auto tick = [&](int slot) {
+    if (PROF) { const long long now = clock64(); pc[slot] += now - tk; tk = now; }
+  };
+  const long long t_start = PROF ? clock64() : 0;
+  using Cfg = Fa2Cfg<KV_ROWS, STAGES, SPLIT>;
+  constexpr int KV_BYTES = Cfg::kKvBytes, SPS = Cfg::kSubsPerSlot, NCTRL = Cfg::kCtrlWarps;
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + FA_Q_BYTES;
+  uint8_t* sV = sK + STAGES * KV_BYTES;
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(sV + STAGES * KV_BYTES);
+  uint64_t* kv_empty = kv_full + STAGES;
+  uint64_t* s_full = kv_empty + STAGES;        // [2]
+  uint64_t* p_full = s_full + 2;               // [2]
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Work order: every full 128-query tile first, the partial last tiles of the (image, head) pairs at the end of the
+  // grid, so the cheap CTAs fill the last wave.
+  const int n_full = S / FA_BM, n_bh = gridDim.x / ((S + FA_BM - 1) / FA_BM);
+  int tile, bh;
+  if (static_cast<int>(blockIdx.x) < n_full * n_bh) {
+    bh = blockIdx.x / n_full;
+    tile = blockIdx.x - bh * n_full;
+  } else {
+    bh = blockIdx.x - n_full * n_bh;
+    tile = n_full;
+  }
+  const int b = bh / H, h = bh - b * H;
+  const int q0 = tile * FA_BM;
+  const int n_blocks = (S + KV_ROWS - 1) / KV_ROWS;   // K/V ring blocks
+  const int n_sub = (S + FA2_SUB - 1) / FA2_SUB;      // 32-key score sub-blocks
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, FA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_wait();   // set-up above overlaps the previous kernel's tail
+
+  // K/V rows [KV_ROWS * j, +KV_ROWS) -> ring slot j % STAGES (+ the Q tile with block 0); whole warp, one lane issues
+  auto load_block = [&](int j) {
+    const int st = j % STAGES;
+    mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES + (j == 0 ? FA_Q_BYTES : 0));
+      if (j == 0) tma_load_3d(sQ, &tmQ, &kv_full[st], h * FA_DH, q0, b);
+      tma_load_3d(sK + st * KV_BYTES, &tmKV, &kv_full[st], D + h * FA_DH, j * KV_ROWS, b);
+      tma_load_3d(sV + st * KV_BYTES, &tmKV, &kv_full[st], 2 * D + h * FA_DH, j * KV_ROWS, b);
+    }
+    __syncwarp();
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ MMA issuer (one elected lane; also the TMA producer if !SPLIT)
+    constexpr uint32_t IDESC_S = make_idesc_f16(FA_BM, FA2_SUB, false, false);
+    constexpr uint32_t IDESC_O = make_idesc_f16(FA_BM, FA_DH, false, true);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t dQ = make_sdesc_sw128(smem_u32(sQ), 0, 1024);           // + k * (32 >> 4) per K step of 16
+    const uint64_t dK0 = make_sdesc_sw128(smem_u32(sK), 0, 1024);          // + slot * (KV_BYTES >> 4) + sub * 256 + k * 2
+    const uint64_t dV0 = make_sdesc_sw128(smem_u32(sV), KV_BYTES, 1024);   // + slot * (KV_BYTES >> 4) + k16 * (2048 >> 4)
+    int loaded = 0;
+    auto issue_s = [&](int t) {   // S_t = Q K_t^T into score buffer t & 1
+      const int jb = t / SPS, sub = t - jb * SPS, st = jb % STAGES, half = t & 1;
+      if (sub == 0) {
+        mbar_wait(&kv_full[st], (jb / STAGES) & 1);
+        tc_fence_after();
+      }
+      const uint64_t dK = dK0 + static_cast<uint64_t>(st * (KV_BYTES >> 4) + sub * ((FA2_SUB * 128) >> 4));
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < FA_DH / 16; ++k)
+          umma_f16(tmem_u + half * FA2_SUB, dQ + 2 * k, dK + 2 * k, IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[half]);
+      }
+      __syncwarp();
+    };
+    if (!SPLIT)
+      while (loaded < STAGES && loaded < n_blocks) load_block(loaded++);
+    issue_s(0);
+    if (n_sub > 1) issue_s(1);
+    if (PROF) tk = clock64();
+    for (int t = 0; t < n_sub; ++t) {
+      const int jb = t / SPS, sub = t - jb * SPS, st = jb % STAGES, half = t & 1;
+      const int nk = (min(FA2_SUB, S - t * FA2_SUB) + 15) / 16;    // chunks of 16 keys that hold a key
+      const bool slot_done = sub == SPS - 1 || t == n_sub - 1;
+      mbar_wait(&p_full[half], (t >> 1) & 1);
+      tc_fence_after();
+      tick(0);
+      const uint64_t dV = dV0 + static_cast<uint64_t>(st * (KV_BYTES >> 4) + sub * 2 * (2048 >> 4));
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < FA2_SUB / 16; ++k)
+          if (k < nk)
+            umma_f16_ts(tmem_u + FA_TMEM_O, tmem_u + half * FA2_SUB + 8 * k, dV + (2048 >> 4) * k, IDESC_O,
+                        (t > 0 || k > 0) ? 1u : 0u);
+        umma_commit(o_full);
+        if (slot_done) umma_commit(&kv_empty[st]);
+      }
+      __syncwarp();
+      // S_{t+2} follows P_t V_t in issue order: the tensor pipe executes in order, so it cannot overwrite P_t early
+      tick(1);
+      if (t + 2 < n_sub) issue_s(t + 2);
+      tick(2);
+      // refill the ring slot this block is draining (a short wait: its last MMA is already running)
+      if (!SPLIT && slot_done && loaded < n_blocks) load_block(loaded++);
+      tick(3);
+    }
+    __syncwarp();
+    if (PROF && lane == 0) {
+      long long* o = prof + 16LL * blockIdx.x;
+      o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3]; o[4] = clock64() - t_start;
+    }
+  } else if (SPLIT && warp == 1) {
+    // ------------------------------------------------ TMA producer
+    for (int j = 0; j < n_blocks; ++j) load_block(j);
+  } else {
+    // ------------------------------------------------ softmax / correction / epilogue: one thread per query row
+    const int row = (warp & 3) * 32 + lane;           // TMEM lane quadrant a warp may touch = warp id % 4
+    const uint32_t sbuf = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t obuf = sbuf + FA_TMEM_O;
+    constexpr float kLazy = 8.0f;
+    const bool warp_has_rows = q0 + (warp & 3) * 32 < S;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    if (PROF) tk = clock64();
+    const long long t_loop = tk;
+    for (int t = 0; t < n_sub; ++t) {
+      const int half = t & 1;
+      mbar_wait(&s_full[half], (t >> 1) & 1);
+      tick(0);
+      if (!warp_has_rows) {          // last query tile of an image: none of this warp's 32 rows exists (their P / O
+        mbar_arrive(&p_full[half]);  // rows stay garbage and are never stored)
+        continue;
+      }
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(sbuf + half * FA2_SUB, r);
+      tmem_ld_wait();
+      tick(1);
+      const int valid = min(FA2_SUB, S - t * FA2_SUB);   // key columns of this sub-block that exist
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (valid == FA2_SUB) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {               // three-input max (sm_100): 16 instead of 32 FMNMX
+          mx0 = fmax3(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) r[i] = 0xff800000u;          // -inf: exp2 -> 0
+          mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+        }
+      }
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));   // finite: the first key of every sub-block exists
+      const bool grow = (m_blk - m_run) * scale_log2 > kLazy;         // true for t == 0 (m_run = -inf)
+      const float m_new = grow ? m_blk : m_run;
+      const float mc = m_new * scale_log2;
+      tick(2);
+      // p = exp2(s * c - m * c) as packed fp16, IN PLACE over the first half of this sub-block's score buffer
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[g * 16 + 2 * i]), scale_log2, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[g * 16 + 2 * i + 1]), scale_log2, -mc));
+          sum0 += p0;
+          sum1 += p1;
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        tmem_st8(sbuf + half * FA2_SUB + g * 8, pk);
+      }
+      tick(3);
+      if (t > 0 && __any_sync(0xffffffffu, grow)) {
+        // O was accumulated against the old maximum: rescale it once P V_{t-1} has retired
+        const float alpha = grow ? fast_exp2((m_run - m_new) * scale_log2) : 1.0f;
+        mbar_wait(o_full, (t - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[16];
+          tmem_ld16(obuf + c * 16, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(obuf + c * 16, o);
+        }
+        l_run *= alpha;
+      }
+      tick(4);
+      l_run += sum0 + sum1;
+      m_run = m_new;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[half]);
+      tick(5);
+    }
+    if (PROF && threadIdx.x == NCTRL * 32) {
+      long long* o = prof + 16LL * blockIdx.x + 5;
+      for (int i = 0; i < 6; ++i) o[i] = pc[i];
+      o[6] = t_loop - t_start;
+      o[7] = clock64() - t_start;
+    }
+    // epilogue: ctx[b, q0 + row, h * 64 ..] = O / l
+    mbar_wait(o_full, (n_sub - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + row;
+    // natural-log log-sum-exp of the scaled scores, for the backward pass (probabilities are recomputed from it)
+    if (lse != nullptr && q < S)
+      lse[(static_cast<long long>(b) * H + h) * S + q] = (m_run * scale_log2 + log2f(l_run)) * 0.6931471805599453f;
+    __half* dst = ctx + (static_cast<long long>(b) * S + q) * D + h * FA_DH;
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) {
+      uint32_t o[16];
+      tmem_ld16(obuf + c0 * 16, o);
+      tmem_ld_wait();
+      if (q < S) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint4 v;
+          __half2 t2;
+          t2 = __floats2half2_rn(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l); v.x = *reinterpret_cast<uint32_t*>(&t2);
+          t2 = __floats2half2_rn(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l); v.y = *reinterpret_cast<uint32_t*>(&t2);
+          t2 = __floats2half2_rn(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l); v.z = *reinterpret_cast<uint32_t*>(&t2);
+          t2 = __floats2half2_rn(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l); v.w = *reinterpret_cast<uint32_t*>(&t2);
+          *reinterpret_cast<uint4*>(dst + c0 * 16 + c * 8) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF = false>
+static int launch_fa2(const void* qkv_f16, void* ctx_f16, float* lse, int B, int S, int H, float sl2, cudaStream_t stream,
+                      long long* prof = nullptr) {
+  using Cfg = Fa2Cfg<KV_ROWS, STAGES, SPLIT>;
+  const int D = H * FA_DH;
+  CUtensorMap tmQ, tmKV;
+  int rc = make_qkv_map(&tmQ, qkv_f16, B, S, D, FA_BM);
+  if (rc) return rc;
+  rc = make_qkv_map(&tmKV, qkv_f16, B, S, D, KV_ROWS);
+  if (rc) return rc;
+  auto kern = flash_attn_fwd2_kernel<KV_ROWS, STAGES, CTAS, SPLIT, PROF>;
+  static bool configured = false;
+  if (!configured) {
+    OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  const unsigned n_cta = static_cast<unsigned>((S + FA_BM - 1) / FA_BM) * H * B;
+  OWL_LAUNCH(kern, n_cta, Cfg::kThreads, Cfg::kSmem, stream, tmQ, tmKV, static_cast<__half*>(ctx_f16), lse, S, D, H, sl2, prof);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
 // Softmax-backward row term (the "delta" of flash attention): delta[b, h, s] = alpha * sum_d dctx[b, s, h*64 + d] *
 // ctx[b, s, h*64 + d]  (= alpha * sum_j P_sj dP_sj).  One thread per 8 consecutive channels, 8 threads per head.
 __global__ void attn_delta_kernel(const __half* __restrict__ ctx, const __half* __restrict__ dctx,
@@ -388,6 +712,25 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse
   OWL_CHECK_ARG(qkv_f16 && ctx_f16 && B > 0 && S > 0 && H > 0, "flash_attn_fwd: bad arguments");
   OWL_CHECK_ARG(head_dim == FA_DH, "flash_attn_fwd: head_dim %d is not built (only 64)", head_dim);
   const int D = H * head_dim;
+  const float sl2 = scale * 1.4426950408889634f;
+  static const int generation = [] {   // OWL_FA_GEN: 1 = first generation; 20..23 = second-generation flavours (A/B timing)
+    const char* e = getenv("OWL_FA_GEN");
+    return e ? atoi(e) : 24;
+  }();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (generation == 94 && g_fa_dbg != nullptr)
+    return launch_fa2<64, 2, 4, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st, g_fa_dbg);
+  if (generation != 1 && g_fa_dbg == nullptr) {
+    switch (generation) {
+      case 20: return launch_fa2<64, 3, 3, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+      case 22: return launch_fa2<32, 4, 4, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+      case 23: return launch_fa2<64, 3, 3, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+      case 24: return launch_fa2<64, 2, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+      case 21: return launch_fa2<32, 4, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+      case 25: return launch_fa2<64, 2, 4, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+      default: return launch_fa2<64, 2, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+    }
+  }
   CUtensorMap tmQ, tmKV;
   int rc = make_qkv_map(&tmQ, qkv_f16, B, S, D, FA_BM);
   if (rc) return rc;
@@ -399,9 +742,8 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse
     configured = true;
   }
   dim3 grid((S + FA_BM - 1) / FA_BM, H, B);
-  const float sl2 = scale * 1.4426950408889634f;
-  OWL_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, static_cast<cudaStream_t>(stream), tmQ,
-               tmKV, static_cast<__half*>(ctx_f16), lse, S, D, sl2, g_fa_dbg);
+  OWL_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, st, tmQ, tmKV, static_cast<__half*>(ctx_f16), lse, S, D,
+             sl2, g_fa_dbg);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

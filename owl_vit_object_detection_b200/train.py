@@ -5,8 +5,11 @@ graph and the optimizer graph.
   step.load(images_host, labels, boxes, num_targets)   async H2D into static device buffers (side stream)
   losses4 = step.run()                                  device tensor [loss_ce, loss_bg, loss_bbox, loss_giou]
 
-CUDA streams and graphs replace a tracing compiler: the ~190 kernels of a step are launched by two graph
-replays; the only host work per step is the NCCL all-reduce call (one flat fp32 buffer).
+CUDA streams and graphs replace a tracing compiler: the ~190 kernels of a step are launched by ONE graph replay
+on a single GPU (forward + loss + backward + AdamW), and by two replays around the NCCL all-reduce call (one flat
+fp32 buffer) under data parallelism.  `run(readback=True)` also queues the 16-byte copy of the four
+losses into pinned host memory; `result(slot)` waits for that copy only, so the host can read step i while step
+i + 1 is already running.
 """
 from __future__ import annotations
 
@@ -33,6 +36,8 @@ class TrainStep:
                 boxes=torch.zeros((batch, max_targets, 4), dtype=torch.float32, device=dev),
                 nt=torch.ones((batch,), dtype=torch.int32, device=dev)))
         self.losses = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(n_input_slots)]
+        self.host_losses = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(n_input_slots)]
+        self.read_done = [torch.cuda.Event() for _ in range(n_input_slots)]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.loaded = [torch.cuda.Event() for _ in range(n_input_slots)]
         self.consumed = [torch.cuda.Event() for _ in range(n_input_slots)]
@@ -90,11 +95,20 @@ class TrainStep:
             return
         state = (self.model.flat_params.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
                  self.optimizer.state.clone())
-        for i in range(len(self.slots)):
-            if self._fwdbwd[i] is None:
-                self._fwdbwd[i] = self._capture(lambda i=i: self._fwd_bwd(i))
-        if self._opt_graph is None:
-            self._opt_graph = self._capture(self.optimizer.step)
+        if self._world == 1:
+            # single GPU: nothing sits between the backward and the optimizer, so the whole step is one graph
+            def whole(i):
+                self._fwd_bwd(i)
+                self.optimizer.step()
+            for i in range(len(self.slots)):
+                if self._fwdbwd[i] is None:
+                    self._fwdbwd[i] = self._capture(lambda i=i: whole(i))
+        else:
+            for i in range(len(self.slots)):
+                if self._fwdbwd[i] is None:
+                    self._fwdbwd[i] = self._capture(lambda i=i: self._fwd_bwd(i))
+            if self._opt_graph is None:
+                self._opt_graph = self._capture(self.optimizer.step)
         # undo the optimizer steps the capture warm-ups made
         self.model.flat_params.copy_(state[0])
         self.optimizer.exp_avg.copy_(state[1])
@@ -102,7 +116,12 @@ class TrainStep:
         self.optimizer.state.copy_(state[3])
         self.model.engine.refresh_shadow()
 
-    def run(self, slot: Optional[int] = None) -> torch.Tensor:
+    def result(self, slot: int):
+        """The four losses of the last `run(slot, readback=True)` as Python floats (waits for that copy only)."""
+        self.read_done[slot].synchronize()
+        return self.host_losses[slot].tolist()
+
+    def run(self, slot: Optional[int] = None, readback: bool = False) -> torch.Tensor:
         if slot is None:
             slot = self._next_run
             self._next_run = (self._next_run + 1) % len(self.slots)
@@ -117,8 +136,11 @@ class TrainStep:
         self.consumed[slot].record(cur)
         if self._world > 1:
             self.model.allreduce_grads(self.group)
-        if self.use_graph:
-            self._opt_graph.replay()
-        else:
+        if not self.use_graph:
             self.optimizer.step()
+        elif self._world > 1:
+            self._opt_graph.replay()
+        if readback:
+            self.host_losses[slot].copy_(self.losses[slot], non_blocking=True)
+            self.read_done[slot].record(cur)
         return self.losses[slot]
