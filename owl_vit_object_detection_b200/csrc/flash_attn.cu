@@ -344,22 +344,35 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Second generation of the forward kernel.  Same row ownership (one softmax thread per query row, 128 TMEM columns
-// per CTA), but the score block is split into 32-key SUB-BLOCKS that ping-pong between two 32-column TMEM buffers:
+// Second generation of the forward kernel (the one the engine runs; the first generation above stays selectable
+// with OWL_FA_GEN=1 for A/B timing).  Same row ownership (one softmax thread per query row, 128 TMEM columns per
+// CTA), but the score block is split into 32-key SUB-BLOCKS that ping-pong between two 32-column TMEM buffers:
 //
 //   TMEM:  S/P buffer 0 @0 (32 cols), S/P buffer 1 @32 (32 cols), O @64 (64 cols);  P_t = 16 packed-fp16 columns
 //          written in place over the first half of its own score buffer
 //   MMA warp:       S_0, S_1;  for t: wait P_t -> O += P_t V_t (2 MMAs, K = 16) -> S_{t+2} = Q K_{t+2}^T (4 MMAs,
 //                   N = 32, into the buffer P_t is being drained from: the tensor pipe executes in order)
-//   softmax thread: for t: wait S_t (issued one whole sub-block ago) -> tcgen05.ld -> max / exp2 / pack ->
-//                   tcgen05.st P_t -> arrive
+//   softmax thread: for t: wait S_t (issued while sub-block t - 1 was being exponentiated) -> tcgen05.ld ->
+//                   three-input max / exp2 / pack -> tcgen05.st P_t -> arrive
 //
 // In the first generation every 64-key block was one serial chain  P arrive -> MMA issue -> MMA -> commit -> TMEM
 // load -> exp2 -> TMEM store -> arrive  per CTA (ncu: tensor 23 %, MUFU 43 %, issue 30 % of active cycles: nothing
 // saturated); here the P.V and score MMAs of the neighbouring sub-blocks run under the exponentials, and the
-// 32-score working set per thread leaves room for FOUR CTAs per SM.
+// 32-score working set per thread (78 registers) leaves room for FOUR CTAs per SM.  The grid is one-dimensional
+// with every full 128-query tile first, so the cheap partial tiles fill the last wave.
+//
+// Measured (tools/fa_prof.py, clock64 per phase, batch 16, S = 577): a softmax thread spends ~1000 clk per sub-block
+// of which the 32 exponentials are XU-bound at 4 warps per scheduler, and waits another ~450 clk for S_t: the MMA
+// warp shares its scheduler with four softmax warps that issue almost every cycle, so its ~60 instructions between
+// "P_t complete" and "S_{t+2} issued" take 500-1000 clk.  Two flavours of that path are built:
+//   rolled (KV_ROWS 64, 2 ring slots, one control warp)        35.0 us at B = 16, S = 577, H = 12 (first gen.: 43.9)
+//   unrolled (compile-time descriptors, one elected region per sub-block for P V + S, K / V arrival waits taken
+//   before the P wait, O committed only for the last two sub-blocks, loads in a producer warp with separate K and
+//   V barriers so a K slot is refilled two sub-blocks earlier)  295 us at B = 4, S = 3601, H = 16 (rolled 321,
+//   first generation 341); 35.4 us at S = 577
 // Template: KV_ROWS = keys per K/V ring slot (32 or 64), STAGES = ring slots, CTAS = CTAs per SM, SPLIT = separate
-// TMA-producer warp (192 threads) instead of one control warp doing both (160 threads).
+// TMA-producer warp (192 threads) instead of one control warp doing both (160 threads), PROF = clock64
+// instrumentation (dev), UNROLL = the unrolled MMA-warp flavour.
 constexpr int FA2_SUB = 32;                          // keys per sub-block
 int make_qkv_map(CUtensorMap* out, const void* qkv, int B, int S, int D, uint32_t box_rows);
 
@@ -372,7 +385,7 @@ struct Fa2Cfg {
   static constexpr int kSubsPerSlot = KV_ROWS / FA2_SUB;
 };
 
-template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF>
+template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF, bool UNROLL>
 __global__ void __launch_bounds__((Fa2Cfg<KV_ROWS, STAGES, SPLIT>::kThreads), CTAS)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        __half* __restrict__ ctx, float* __restrict__ lse, int S, int D, int H, float scale_log2,
@@ -384,6 +397,9 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     if (PROF) { const long long now = clock64(); pc[slot] += now - tk; tk = now; }
   };
   const long long t_start = PROF ? clock64() : 0;
+  auto stamp = [&](int idx) {   // CTA 0 only: raw clock64 of loop events -> prof[16 * gridDim.x + idx]
+    if (PROF && blockIdx.x == 0) prof[16LL * gridDim.x + idx] = clock64();
+  };
   using Cfg = Fa2Cfg<KV_ROWS, STAGES, SPLIT>;
   constexpr int KV_BYTES = Cfg::kKvBytes, SPS = Cfg::kSubsPerSlot, NCTRL = Cfg::kCtrlWarps;
   extern __shared__ uint8_t fa_smem_raw[];
@@ -393,10 +409,13 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* sV = sK + STAGES * KV_BYTES;
   uint64_t* kv_full = reinterpret_cast<uint64_t*>(sV + STAGES * KV_BYTES);
   uint64_t* kv_empty = kv_full + STAGES;
-  uint64_t* s_full = kv_empty + STAGES;        // [2]
+  uint64_t* v_full = kv_empty + STAGES;        // UNROLL flavour: K and V have their own barriers (kv_* = K)
+  uint64_t* v_empty = v_full + STAGES;
+  uint64_t* s_full = v_empty + STAGES;         // [2]
   uint64_t* p_full = s_full + 2;               // [2]
-  uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_full + 2;               // [2]: rolled flavour uses [0] every sub-block; unrolled: [0] = P V of the
+                                               // last-but-one sub-block, [1] = of the last (each completes once)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work order: every full 128-query tile first, the partial last tiles of the (image, head) pairs at the end of the
@@ -418,9 +437,13 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+      mbar_init(&v_full[s], 1);  mbar_init(&v_empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -443,6 +466,30 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (j == 0) tma_load_3d(sQ, &tmQ, &kv_full[st], h * FA_DH, q0, b);
       tma_load_3d(sK + st * KV_BYTES, &tmKV, &kv_full[st], D + h * FA_DH, j * KV_ROWS, b);
       tma_load_3d(sV + st * KV_BYTES, &tmKV, &kv_full[st], 2 * D + h * FA_DH, j * KV_ROWS, b);
+    }
+    __syncwarp();
+  };
+
+  // UNROLL flavour: K block j (+ the Q tile with block 0) and V block j travel separately.  A K slot is free as soon
+  // as the two score MMAs that read it have retired, two sub-blocks before the P.V MMAs release the V slot, so both
+  // refills get two sub-blocks of lead over their first use (the shared barrier left the K load ~600 clk: the
+  // score MMA of every other sub-block waited ~450 clk for its keys).
+  auto load_k = [&](int j) {
+    const int st = j % STAGES;
+    mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(&kv_full[st], KV_BYTES + (j == 0 ? FA_Q_BYTES : 0));
+      if (j == 0) tma_load_3d(sQ, &tmQ, &kv_full[st], h * FA_DH, q0, b);
+      tma_load_3d(sK + st * KV_BYTES, &tmKV, &kv_full[st], D + h * FA_DH, j * KV_ROWS, b);
+    }
+    __syncwarp();
+  };
+  auto load_v = [&](int j) {
+    const int st = j % STAGES;
+    mbar_wait(&v_empty[st], ((j / STAGES) & 1) ^ 1);
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(&v_full[st], KV_BYTES);
+      tma_load_3d(sV + st * KV_BYTES, &tmKV, &v_full[st], 2 * D + h * FA_DH, j * KV_ROWS, b);
     }
     __syncwarp();
   };
@@ -471,6 +518,66 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       __syncwarp();
     };
+    if constexpr (UNROLL) {
+      // The MMA warp shares its scheduler with four softmax warps that issue almost every cycle, so each of its
+      // instructions costs 10-20 clk and everything between "P_t complete" and "S_{t+2} issued" is on the critical
+      // path of the softmax threads (measured: 500-1000 clk, the threads waited a third of the time).  Therefore:
+      //  * the loop is unrolled over one trip around the K/V ring: ring slot, score buffer and descriptor offsets
+      //    are compile-time constants of the unrolled body;
+      //  * the K / V arrival waits are taken BEFORE the wait for P_t (the data landed long ago);
+      //  * P_t V_t, S_{t+2} and their commits leave in ONE elected region;
+      //  * O gets its own commit only for the last two sub-blocks (the rare rescale waits on the S commit that
+      //    follows P V instead); the loads live in the producer warp.
+      static_assert(SPLIT, "the unrolled flavour takes its loads from the producer warp");
+      constexpr int PERIOD = STAGES * SPS;
+      static_assert(PERIOD % 2 == 0, "the score-buffer parity must repeat with the ring");
+      const int nk_last = (S - (n_sub - 1) * FA2_SUB + 15) / 16;
+      auto score = [&](int slot2, int sub2, int half2, bool release) {   // S = Q K^T of one sub-block (elected lane)
+        const uint64_t dK = dK0 + static_cast<uint64_t>(slot2 * (KV_BYTES >> 4) + sub2 * ((FA2_SUB * 128) >> 4));
+#pragma unroll
+        for (int k = 0; k < FA_DH / 16; ++k)
+          umma_f16(tmem_u + half2 * FA2_SUB, dQ + 2 * k, dK + 2 * k, IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[half2]);
+        if (release) umma_commit(&kv_empty[slot2]);
+      };
+      mbar_wait(&kv_full[0], 0);
+      if (SPS == 1 && n_sub > 1) mbar_wait(&kv_full[1 % STAGES], 0);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        score(0, 0, 0, SPS == 1 || n_sub == 1);
+        if (n_sub > 1) score((1 / SPS) % STAGES, 1 % SPS, 1, 1 % SPS == SPS - 1 || n_sub == 2);
+      }
+      __syncwarp();
+      int ring = 0;
+      for (int t0 = 0; t0 < n_sub; t0 += PERIOD, ++ring) {
+#pragma unroll
+        for (int u = 0; u < PERIOD; ++u) {
+          const int t = t0 + u;
+          if (t >= n_sub) break;
+          const int slot = (u / SPS) % STAGES, sub = u % SPS, half = u & 1;
+          const int u2 = (u + 2) % PERIOD, wrap = (u + 2) / PERIOD;
+          const int slot2 = (u2 / SPS) % STAGES, sub2 = u2 % SPS;
+          const bool last = t == n_sub - 1, more = t + 2 < n_sub;
+          if (sub == 0) mbar_wait(&v_full[slot], ring & 1);                           // V of sub-block t
+          if (more && sub2 == 0) mbar_wait(&kv_full[slot2], (ring + wrap) & 1);       // K of sub-block t + 2
+          mbar_wait(&p_full[half], ((t0 >> 1) + (u >> 1)) & 1);
+          tc_fence_after();
+          if (lane == 0) stamp(t * 8 + 0);
+          const uint64_t dV = dV0 + static_cast<uint64_t>(slot * (KV_BYTES >> 4) + sub * 2 * (2048 >> 4));
+          if (elect_one_sync()) {
+            umma_f16_ts(tmem_u + FA_TMEM_O, tmem_u + half * FA2_SUB, dV, IDESC_O, (u > 0 || t0 > 0) ? 1u : 0u);
+            if (!last || nk_last > 1)
+              umma_f16_ts(tmem_u + FA_TMEM_O, tmem_u + half * FA2_SUB + 8, dV + (2048 >> 4), IDESC_O, 1u);
+            if (t + 2 >= n_sub) umma_commit(&o_full[last ? 1 : 0]);
+            if (sub == SPS - 1 || last) umma_commit(&v_empty[slot]);
+            // S_{t+2} follows P_t V_t in issue order: the tensor pipe executes in order, so it cannot overwrite P_t
+            if (more) score(slot2, sub2, half, sub2 == SPS - 1 || t + 2 == n_sub - 1);
+          }
+          __syncwarp();
+          if (lane == 0) stamp(t * 8 + 2);
+        }
+      }
+    } else {
     if (!SPLIT)
       while (loaded < STAGES && loaded < n_blocks) load_block(loaded++);
     issue_s(0);
@@ -483,6 +590,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(&p_full[half], (t >> 1) & 1);
       tc_fence_after();
       tick(0);
+      if (lane == 0) stamp(t * 8 + 0);
       const uint64_t dV = dV0 + static_cast<uint64_t>(st * (KV_BYTES >> 4) + sub * 2 * (2048 >> 4));
       if (elect_one_sync()) {
 #pragma unroll
@@ -496,11 +604,15 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       __syncwarp();
       // S_{t+2} follows P_t V_t in issue order: the tensor pipe executes in order, so it cannot overwrite P_t early
       tick(1);
+      if (lane == 0) stamp(t * 8 + 1);
       if (t + 2 < n_sub) issue_s(t + 2);
       tick(2);
+      if (lane == 0) stamp(t * 8 + 2);
       // refill the ring slot this block is draining (a short wait: its last MMA is already running)
       if (!SPLIT && slot_done && loaded < n_blocks) load_block(loaded++);
       tick(3);
+      if (lane == 0) stamp(t * 8 + 3);
+    }
     }
     __syncwarp();
     if (PROF && lane == 0) {
@@ -509,7 +621,11 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
   } else if (SPLIT && warp == 1) {
     // ------------------------------------------------ TMA producer
-    for (int j = 0; j < n_blocks; ++j) load_block(j);
+    if constexpr (UNROLL) {
+      for (int j = 0; j < n_blocks; ++j) { load_k(j); load_v(j); }
+    } else {
+      for (int j = 0; j < n_blocks; ++j) load_block(j);
+    }
   } else {
     // ------------------------------------------------ softmax / correction / epilogue: one thread per query row
     const int row = (warp & 3) * 32 + lane;           // TMEM lane quadrant a warp may touch = warp id % 4
@@ -525,6 +641,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int half = t & 1;
       mbar_wait(&s_full[half], (t >> 1) & 1);
       tick(0);
+      if (threadIdx.x == NCTRL * 32) stamp(t * 8 + 4);
       if (!warp_has_rows) {          // last query tile of an image: none of this warp's 32 rows exists (their P / O
         mbar_arrive(&p_full[half]);  // rows stay garbage and are never stored)
         continue;
@@ -534,6 +651,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tmem_ld32(sbuf + half * FA2_SUB, r);
       tmem_ld_wait();
       tick(1);
+      if (threadIdx.x == NCTRL * 32) stamp(t * 8 + 5);
       const int valid = min(FA2_SUB, S - t * FA2_SUB);   // key columns of this sub-block that exist
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
       if (valid == FA2_SUB) {
@@ -573,10 +691,13 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_st8(sbuf + half * FA2_SUB + g * 8, pk);
       }
       tick(3);
+      if (threadIdx.x == NCTRL * 32) stamp(t * 8 + 6);
       if (t > 0 && __any_sync(0xffffffffu, grow)) {
         // O was accumulated against the old maximum: rescale it once P V_{t-1} has retired
         const float alpha = grow ? fast_exp2((m_run - m_new) * scale_log2) : 1.0f;
-        mbar_wait(o_full, (t - 1) & 1);
+        if (!UNROLL) mbar_wait(o_full, (t - 1) & 1);
+        else if (t + 1 < n_sub) mbar_wait(&s_full[half ^ 1], ((t + 1) >> 1) & 1);   // S_{t+1} was committed after P V_{t-1}
+        else mbar_wait(o_full, 0);                                                  // last sub-block: P V_{t-1} has its own commit
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -596,6 +717,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       mbar_arrive(&p_full[half]);
       tick(5);
+      if (threadIdx.x == NCTRL * 32) stamp(t * 8 + 7);
     }
     if (PROF && threadIdx.x == NCTRL * 32) {
       long long* o = prof + 16LL * blockIdx.x + 5;
@@ -604,7 +726,8 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       o[7] = clock64() - t_start;
     }
     // epilogue: ctx[b, q0 + row, h * 64 ..] = O / l
-    mbar_wait(o_full, (n_sub - 1) & 1);
+    if (UNROLL) mbar_wait(&o_full[1], 0);
+    else mbar_wait(o_full, (n_sub - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int q = q0 + row;
@@ -640,7 +763,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF = false>
+template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF = false, bool UNROLL = false>
 static int launch_fa2(const void* qkv_f16, void* ctx_f16, float* lse, int B, int S, int H, float sl2, cudaStream_t stream,
                       long long* prof = nullptr) {
   using Cfg = Fa2Cfg<KV_ROWS, STAGES, SPLIT>;
@@ -650,7 +773,7 @@ static int launch_fa2(const void* qkv_f16, void* ctx_f16, float* lse, int B, int
   if (rc) return rc;
   rc = make_qkv_map(&tmKV, qkv_f16, B, S, D, KV_ROWS);
   if (rc) return rc;
-  auto kern = flash_attn_fwd2_kernel<KV_ROWS, STAGES, CTAS, SPLIT, PROF>;
+  auto kern = flash_attn_fwd2_kernel<KV_ROWS, STAGES, CTAS, SPLIT, PROF, UNROLL>;
   static bool configured = false;
   if (!configured) {
     OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -713,23 +836,24 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse
   OWL_CHECK_ARG(head_dim == FA_DH, "flash_attn_fwd: head_dim %d is not built (only 64)", head_dim);
   const int D = H * head_dim;
   const float sl2 = scale * 1.4426950408889634f;
-  static const int generation = [] {   // OWL_FA_GEN: 1 = first generation; 20..23 = second-generation flavours (A/B timing)
+  // Flavour: 0 (default) picks by sequence length; OWL_FA_GEN = 1 first generation, 24 / 26 force a flavour of the
+  // second (A/B timing), 94 / 95 the instrumented builds of 24 / 26 (tools/fa_prof.py).
+  //   24 = rolled MMA loop, one control warp, shared K/V barrier: best at S = 577 (35.0 us at batch 16; 26: 35.4)
+  //   26 = unrolled MMA loop, producer warp, separate K / V barriers: best on long sequences (S = 3601, B = 4,
+  //        H = 16: 295 us; 24: 321 us; first generation: 341 us)
+  static const int generation = [] {
     const char* e = getenv("OWL_FA_GEN");
-    return e ? atoi(e) : 24;
+    return e ? atoi(e) : 0;
   }();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (generation == 95 && g_fa_dbg != nullptr)
+    return launch_fa2<64, 2, 4, true, true, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st, g_fa_dbg);
   if (generation == 94 && g_fa_dbg != nullptr)
     return launch_fa2<64, 2, 4, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st, g_fa_dbg);
   if (generation != 1 && g_fa_dbg == nullptr) {
-    switch (generation) {
-      case 20: return launch_fa2<64, 3, 3, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      case 22: return launch_fa2<32, 4, 4, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      case 23: return launch_fa2<64, 3, 3, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      case 24: return launch_fa2<64, 2, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      case 21: return launch_fa2<32, 4, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      case 25: return launch_fa2<64, 2, 4, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      default: return launch_fa2<64, 2, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    }
+    const bool long_seq = generation == 26 || (generation != 24 && S > 1024);
+    if (long_seq) return launch_fa2<64, 2, 4, true, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+    return launch_fa2<64, 2, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
   }
   CUtensorMap tmQ, tmKV;
   int rc = make_qkv_map(&tmQ, qkv_f16, B, S, D, FA_BM);
