@@ -370,6 +370,11 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 //   before the P wait, O committed only for the last two sub-blocks, loads in a producer warp with separate K and
 //   V barriers so a K slot is refilled two sub-blocks earlier)  295 us at B = 4, S = 3601, H = 16 (rolled 321,
 //   first generation 341); 35.4 us at S = 577
+// Tried and dropped: (a) pulling S_{t+1} into registers before exponentiating S_t (59.5 us: S_{t+1} is only issued
+// after P_{t-1}, so the wait moved in front of the work); (b) a two-CTAs-per-SM layout with 256 TMEM columns (64-key
+// double-buffered S, P in columns of its own, so the next score MMA only waits for the scores to be read out):
+// 48.2 us at S = 577 and 388 us at S = 3601 - with two softmax warps per scheduler nothing hides the TMEM load /
+// store / barrier latencies of a thread, and 960 CTAs become 3.2 waves of 296.
 // Template: KV_ROWS = keys per K/V ring slot (32 or 64), STAGES = ring slots, CTAS = CTAs per SM, SPLIT = separate
 // TMA-producer warp (192 threads) instead of one control warp doing both (160 threads), PROF = clock64
 // instrumentation (dev), UNROLL = the unrolled MMA-warp flavour.
