@@ -26,6 +26,13 @@ const char* owl_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
 int owl_abi_version(void);
 
+/* L2 persistence window (no reference counterpart: the reference's residual stream is whatever ATen allocates).
+ * Every later launch of this library tags accesses to [base, base + bytes) as persisting in the L2 set-aside
+ * (cudaLaunchAttributeAccessPolicyWindow); the set-aside is sized to the window (capped by the device limits).
+ * The engine points it at the fp32 residual stream of the encoder (HF:490-511: read by both LayerNorms and both
+ * residual adds of a layer).  base = NULL or bytes <= 0 clears it.  Call it outside stream capture. */
+int owl_l2_persist(const void* base, long long bytes, float hit_ratio);
+
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05 + TMEM + TMA).  Replaces every nn.Linear / Conv2d / matmul on the path:
  * HF:336 (patch embed), HF:439-441 (q,k,v), HF:459 (out_proj), HF:474-476 (MLP), HF:1020-1024 (box

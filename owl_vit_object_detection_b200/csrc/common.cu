@@ -67,6 +67,9 @@ int make_tensor_map_f16(CUtensorMap* out, const void* base, uint64_t inner, uint
   return OWL_OK;
 }
 
+static L2Window g_l2_window = {nullptr, 0, 0.f};
+const L2Window& l2_window() { return g_l2_window; }
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -89,4 +92,32 @@ int num_sms() {
 }  // namespace owl
 
 extern "C" const char* owl_last_error(void) { return owl::g_err; }
-extern "C" int owl_abi_version(void) { return 3; }
+extern "C" int owl_abi_version(void) { return 4; }
+
+extern "C" int owl_l2_persist(const void* base, long long bytes, float hit_ratio) {
+  using namespace owl;
+  static long long limit_set = -1;
+  if (base == nullptr || bytes <= 0) {
+    g_l2_window = {nullptr, 0, 0.f};
+    return OWL_OK;
+  }
+  int dev = 0, max_persist = 0, max_window = 0;
+  OWL_CUDA(cudaGetDevice(&dev));
+  OWL_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  OWL_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  if (max_persist <= 0 || max_window <= 0) {       // no set-aside on this device: leave the launches untagged
+    g_l2_window = {nullptr, 0, 0.f};
+    return OWL_OK;
+  }
+  const long long win = bytes < max_window ? bytes : max_window;
+  const long long want = win < max_persist ? win : max_persist;
+  if (want != limit_set) {   // not capturable: callers set the window before they capture a graph (Engine.forward)
+    OWL_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(want)));
+    limit_set = want;
+  }
+  // a window larger than the set-aside is sampled with hit_ratio so the persisting lines do not thrash each other
+  float ratio = hit_ratio > 0.f ? hit_ratio : 1.0f;
+  if (win > want) ratio *= static_cast<float>(want) / static_cast<float>(win);
+  g_l2_window = {const_cast<void*>(base), static_cast<size_t>(win), ratio};
+  return OWL_OK;
+}

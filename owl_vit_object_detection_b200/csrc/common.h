@@ -50,6 +50,12 @@ int num_sms();
 // fill / drain bubbles are a measurable part of it.  OWL_PDL=0 in the environment turns the attribute off.
 bool pdl_enabled();
 
+// L2 persistence: one address window (the fp32 residual stream, read three times and written twice per encoder layer)
+// is tagged cudaAccessPropertyPersisting on every launch of this library (owl_l2_persist, common.cu), so it stays in
+// the L2 set-aside instead of being evicted by the streaming GEMM operands between its uses.
+struct L2Window { void* base; size_t bytes; float hit_ratio; };
+const L2Window& l2_window();
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                        int cluster_x, Args&&... args) {
@@ -58,8 +64,18 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  const L2Window& w = l2_window();
+  if (w.bytes > 0) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = w.base;
+    attr[n].val.accessPolicyWindow.num_bytes = w.bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = w.hit_ratio;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    ++n;
+  }
   if (pdl_enabled()) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;

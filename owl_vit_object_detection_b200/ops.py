@@ -132,6 +132,24 @@ def softmax_rows_f16(scores: torch.Tensor, *, rows: int, n: int, ld: int):
     return scores
 
 
+_L2_WINDOW = (0, 0)
+
+
+def l2_persist(t: Optional[torch.Tensor], hit_ratio: float = 1.0) -> None:
+    """Tag `t`'s storage as L2-persisting for every later launch (owl_l2_persist); None clears the window.
+    OWL_L2_PERSIST=0 in the environment disables it (A/B timing)."""
+    global _L2_WINDOW
+    import os
+    if os.environ.get("OWL_L2_PERSIST", "1") == "0":
+        return
+    key = (0, 0) if t is None else (t.data_ptr(), t.numel() * t.element_size())
+    if key == _L2_WINDOW:
+        return
+    check(lib().owl_l2_persist(ctypes.c_void_p(key[0]), ctypes.c_longlong(key[1]), ctypes.c_float(hit_ratio)),
+          "owl_l2_persist")
+    _L2_WINDOW = key
+
+
 def flash_attn_fwd(qkv16: torch.Tensor, ctx16: torch.Tensor, *, B: int, S: int, H: int, head_dim: int, scale: float,
                    lse: Optional[torch.Tensor] = None):
     """ctx = softmax(scale q k^T) v per (image, head); optionally lse [B, H, S] fp32 (natural log) for the backward."""
