@@ -158,3 +158,31 @@ def test_large_batch_uses_warp_per_image_solver():
         exp = torch.full((T,), -1, dtype=torch.int32)
         exp[torch.from_numpy(cols)] = torch.from_numpy(rows).int()
         assert torch.equal(match[b], exp), b
+
+
+def test_image_without_targets():
+    """An image with zero targets (reference: `linear_sum_assignment` on a 576 x 0 matrix returns no pair; the box
+    losses divide by num_boxes = 0 and the positive class term averages over no rows -> nan, exactly where the oracle
+    has nan) must not disturb its neighbours in the batch: their indices and losses stay exact."""
+    cfg = synth.B32
+    B = 4
+    labels, tboxes, nt = synth.make_targets(cfg, B, seed=21)
+    nt[2] = 0
+    labels[2], tboxes[2] = -1, 0.0
+    sims, pred, _, _ = synth.make_matcher_inputs(B, 5, seed=22)
+    scales = synth.make_class_scales(cfg)
+    costT, match, out, dsims, dboxes = _run_device(sims, pred, labels, tboxes, nt, scales)
+    assert (match[2] == -1).all() and (out["pred_sorted"][2] == -1).all() and (out["tgt_sorted"][2] == -1).all()
+    assert (out["tc_matched"][2] == cfg.n_classes).all() and (out["tc_final"][2] == cfg.n_classes).all()
+    for b in range(B):
+        t = int(nt[b])
+        l, tc_final, inds = mo.push_pull_loss(sims[b:b + 1], pred[b:b + 1], [labels[b, :t]], [tboxes[b, :t]],
+                                              cfg.n_classes, scales)
+        assert out["pred_sorted"][b, :t].tolist() == inds[0][0].tolist()
+        assert out["tgt_sorted"][b, :t].tolist() == inds[0][1].tolist()
+        assert torch.equal(out["tc_final"][b], tc_final[0])
+        got = out["losses_per_image"][b, :4].numpy()
+        ref = np.array([l[k].item() for k in ("loss_ce", "loss_bg", "loss_bbox", "loss_giou")], dtype=np.float32)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (b, got, ref)
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-6, equal_nan=True)
+    assert np.isfinite(out["losses_per_image"][[0, 1, 3], :4].numpy()).all()
