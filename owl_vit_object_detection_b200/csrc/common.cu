@@ -96,23 +96,26 @@ extern "C" int owl_abi_version(void) { return 4; }
 
 extern "C" int owl_l2_persist(const void* base, long long bytes, float hit_ratio) {
   using namespace owl;
+  // Best effort: the window is a hint.  Any failure (no set-aside on the device, a limit the driver refuses, MIG)
+  // leaves the launches untagged instead of failing the caller.
   static long long limit_set = -1;
-  if (base == nullptr || bytes <= 0) {
-    g_l2_window = {nullptr, 0, 0.f};
-    return OWL_OK;
-  }
+  g_l2_window = {nullptr, 0, 0.f};
+  if (base == nullptr || bytes <= 0) return OWL_OK;
   int dev = 0, max_persist = 0, max_window = 0;
-  OWL_CUDA(cudaGetDevice(&dev));
-  OWL_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
-  OWL_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-  if (max_persist <= 0 || max_window <= 0) {       // no set-aside on this device: leave the launches untagged
-    g_l2_window = {nullptr, 0, 0.f};
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess ||
+      max_persist <= 0 || max_window <= 0) {
+    (void)cudaGetLastError();
     return OWL_OK;
   }
   const long long win = bytes < max_window ? bytes : max_window;
   const long long want = win < max_persist ? win : max_persist;
   if (want != limit_set) {   // not capturable: callers set the window before they capture a graph (Engine.forward)
-    OWL_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(want)));
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(want)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return OWL_OK;
+    }
     limit_set = want;
   }
   // a window larger than the set-aside is sampled with hit_ratio so the persisting lines do not thrash each other
