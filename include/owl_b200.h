@@ -29,8 +29,8 @@ int owl_abi_version(void);
 /* L2 persistence window (no reference counterpart: the reference's residual stream is whatever ATen allocates).
  * Every later launch of this library tags accesses to [base, base + bytes) as persisting in the L2 set-aside
  * (cudaLaunchAttributeAccessPolicyWindow); the set-aside is sized to the window (capped by the device limits).
- * The engine points it at the fp32 residual stream of the encoder (HF:490-511: read by both LayerNorms and both
- * residual adds of a layer).  base = NULL or bytes <= 0 clears it.  Best effort: where the device refuses the
+ * The engine can point it at the fp32 residual stream of the encoder (HF:490-511: read by both LayerNorms and both
+ * residual adds of a layer; opt-in, measured neutral on B200).  base = NULL or bytes <= 0 clears it.  Best effort: where the device refuses the
  * set-aside the launches simply stay untagged (always returns 0).  Call it outside stream capture. */
 int owl_l2_persist(const void* base, long long bytes, float hit_ratio);
 

@@ -189,7 +189,7 @@ class Engine:
         Q, C, eps = cfg.n_queries, cfg.n_classes, cfg.ln_eps
         self.sync_shadow()
         ws = self.workspace(B)
-        ops.l2_persist(ws.x)      # the fp32 residual stream stays in the L2 set-aside between its five uses per layer
+        ops.l2_persist(ws.x)      # opt-in (OWL_L2_PERSIST=1): keep the fp32 residual stream in the L2 set-aside
         M, MP = B * S, B * P
 
         # ---- embeddings HF:334-344 + pre_layernorm HF:768

@@ -137,10 +137,11 @@ _L2_WINDOW = (0, 0)
 
 def l2_persist(t: Optional[torch.Tensor], hit_ratio: float = 1.0) -> None:
     """Tag `t`'s storage as L2-persisting for every later launch (owl_l2_persist); None clears the window.
-    OWL_L2_PERSIST=0 in the environment disables it (A/B timing)."""
+    Opt-in with OWL_L2_PERSIST=1: on B200 the step time with and without the window is the same within the
+    run-to-run noise (3.594 / 3.597 ms with, 3.602 / 3.575 ms without, same box, 30 steps each)."""
     global _L2_WINDOW
     import os
-    if os.environ.get("OWL_L2_PERSIST", "1") == "0":
+    if os.environ.get("OWL_L2_PERSIST", "0") != "1":
         return
     key = (0, 0) if t is None else (t.data_ptr(), t.numel() * t.element_size())
     if key == _L2_WINDOW:
