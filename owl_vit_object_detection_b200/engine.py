@@ -122,6 +122,14 @@ class Workspace:
         return self._bw
 
 
+def alias_version(flat: torch.Tensor, aliases) -> int:
+    """Sum of the autograd version counters of a flat buffer and of tensors that alias it (Engine.version)."""
+    v = flat._version
+    for t in aliases:
+        v += t._version
+    return v
+
+
 class Engine:
     def __init__(self, cfg: OwlConfig, layout: ParamLayout, flat32: torch.Tensor):
         assert flat32.is_cuda and flat32.dtype == torch.float32 and flat32.numel() == layout.total
@@ -135,8 +143,21 @@ class Engine:
         self.patch_w16 = torch.zeros((cfg.hidden, self.Kp), dtype=torch.float16, device=self.device)
         self.box_bias = _box_bias(cfg, self.device)
         self._ws: Dict[int, Workspace] = {}
+        self._watch: list = []          # tensors aliasing flat32 that carry version counters of their own (watch())
         self._shadow_version = None
         self.refresh_shadow()
+
+    def watch(self, tensors) -> None:
+        """Tensors aliasing `flat32` whose own version counters must also invalidate the fp16 shadow.  The
+        nn.Parameter views share `flat32`'s counter only until `Module.to()` re-points them through `.data =`
+        (set_data leaves a tensor with a counter of its own): from then on an in-place update by torch.optim
+        (reference main.py:56-60,91) bumps the parameter's counter, not the flat buffer's."""
+        self._watch = list(tensors)
+        self._shadow_version = self.version()
+
+    def version(self) -> int:
+        """Changes whenever flat32 or a watched alias was modified in place through torch."""
+        return alias_version(self.flat32, self._watch)
 
     # ------------------------------------------------------------------ parameters
     def p32(self, name: str) -> torch.Tensor:
@@ -156,10 +177,10 @@ class Engine:
                 self.patch_w16 = w
             else:
                 self.patch_w16[:, :K].copy_(w)
-        self._shadow_version = self.flat32._version
+        self._shadow_version = self.version()
 
     def sync_shadow(self) -> None:
-        if self.flat32._version != self._shadow_version:
+        if self.version() != self._shadow_version:
             self.refresh_shadow()
 
     def workspace(self, B: int) -> Workspace:

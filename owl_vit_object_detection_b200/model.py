@@ -157,6 +157,8 @@ class OwlViT(nn.Module):
                 raise RuntimeError("OwlViT runs on hand-written sm_100a kernels only: move the model to a CUDA "
                                    "device first (there is no CPU fallback)")
             self._engine = Engine(self.cfg, self.layout, self._flat)
+            # the parameters alias the flat buffer but may carry version counters of their own (after .to())
+            self._engine.watch([self._param(n) for n in self._names])
         return self._engine
 
     @property
@@ -265,4 +267,4 @@ class FusedAdamW:
                   beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
                   state=self.state, grad_mul=self.grad_mul)
         # the kernel wrote params through a raw pointer: tell the engine its fp16 shadow is already current
-        eng._shadow_version = m.flat_params._version
+        eng._shadow_version = eng.version()

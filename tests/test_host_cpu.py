@@ -120,3 +120,40 @@ def test_allreduce_flat_grads_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2, r.stdout
+
+
+def test_shadow_version_tracks_parameters_after_module_to():
+    """The fp16 GEMM operands are refreshed when `Engine.version()` changes.  After `Module.to()` the parameters are
+    re-pointed at the moved flat buffer through `.data =`, which leaves them with version counters of their own: an
+    in-place torch.optim.AdamW step (the reference's optimizer, main.py:56-60,91) then changes the flat buffer's
+    contents without touching its counter, so the version must also watch the parameters."""
+    import torch
+    from owl_vit_object_detection_b200 import synth
+    from owl_vit_object_detection_b200.engine import alias_version
+    from owl_vit_object_detection_b200.model import OwlViT
+    cfg = synth.TINY
+    sd = synth.make_weights(cfg, seed=1)
+    model = OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg)
+    model._apply(lambda t: t.clone())                       # what .to(device) does: a new flat buffer
+    flat = model.flat_params
+    params = [model._param(n) for n in model._names]
+    assert all(p.data_ptr() >= flat.data_ptr() and p.data_ptr() < flat.data_ptr() + flat.numel() * 4 for p in params)
+    before_values = flat.clone()
+    v_flat, v_all = flat._version, alias_version(flat, params)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.1)
+    for p in model.parameters():
+        if p.requires_grad:
+            p.grad = torch.ones_like(p)
+    opt.step()
+    assert not torch.equal(flat, before_values), "the optimizer writes through the views into the flat buffer"
+    assert alias_version(flat, params) != v_all, "Engine.version() must see an in-place torch.optim step"
+    if flat._version == v_flat:
+        # the case the watch exists for: set_data() un-shared the counters
+        assert any(p._version > 0 for p in params)
+    # a model that was never moved shares one counter between the flat buffer and its parameter views
+    model2 = OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg)
+    p0 = model2._param("queries")
+    v0 = alias_version(model2.flat_params, [p0])
+    with torch.no_grad():
+        p0.mul_(0.5)
+    assert alias_version(model2.flat_params, [p0]) != v0
