@@ -74,6 +74,8 @@ def check(rc: int, what: str, kernels: int = 1) -> None:
 
 
 def stream_ptr() -> int:
+    """The current torch stream of the CURRENT device.  Kernels are launched on the current device: callers that hold
+    tensors of another device enter `torch.cuda.device(t.device)` first (Engine / the loss classes do)."""
     import torch
     return torch.cuda.current_stream().cuda_stream
 

@@ -291,11 +291,8 @@ extern "C" int owl_attn_bwd(const void* qkv_f16, const void* dctx_f16, const flo
   rc = make_tensor_map_f16(&tmDO, dctx_f16, static_cast<uint64_t>(D), static_cast<uint64_t>(S), static_cast<uint64_t>(B),
                            static_cast<uint64_t>(D), static_cast<uint64_t>(S) * D, AB_DH, AB_T);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    OWL_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  OWL_CUDA(ensure_smem(optin, attn_bwd_kernel, AB_SMEM));
   OWL_CUDA(cudaMemsetAsync(dq32, 0, sizeof(float) * static_cast<size_t>(B) * S * D, s));
   dim3 grid((S + AB_T - 1) / AB_T, H, B);
   OWL_LAUNCH(attn_bwd_kernel, grid, AB_THREADS, AB_SMEM, s, tmQKV, tmDO, lse, delta, static_cast<__half*>(dqkv_f16), dq32,

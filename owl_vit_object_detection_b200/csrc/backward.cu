@@ -625,12 +625,8 @@ extern "C" int owl_post_fuse_bwd(const float* x, const float* ecls, const float*
   dim3 grid((P + rows_per_cta - 1) / rows_per_cta, B);
 #define OWL_PFB_CASE(NV)                                                                                             \
   case NV: {                                                                                                         \
-    static bool configured = false;                                                                                  \
-    if (!configured) {                                                                                               \
-      OWL_CUDA(cudaFuncSetAttribute(post_fuse_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                    static_cast<int>(smem)));                                                        \
-      configured = true;                                                                                             \
-    }                                                                                                                \
+    static SmemOptIn optin;                                                                                          \
+    OWL_CUDA(ensure_smem(optin, post_fuse_bwd_kernel<NV>, smem));                                                    \
     OWL_LAUNCH(post_fuse_bwd_kernel<NV>, grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream), x, ecls, g1, \
                b1, g2, dfeats, dx, dcl, dg1, db1, dg2, db2, P, eps, rows_per_cta, gscale);                          \
   } break;

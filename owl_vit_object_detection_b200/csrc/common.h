@@ -42,6 +42,23 @@ int make_tensor_map_f16(CUtensorMap* out, const void* base, uint64_t inner, uint
 
 int num_sms();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a process that drives several GPUs has to opt in on
+// each of them.  One SmemOptIn per call site (kernel instantiation) remembers the largest size configured per device.
+struct SmemOptIn { size_t bytes[64] = {}; };
+template <class Kernel>
+cudaError_t ensure_smem(SmemOptIn& st, Kernel kernel, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  dev &= 63;
+  if (bytes > st.bytes[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return e;
+    st.bytes[dev] = bytes;
+  }
+  return cudaSuccess;
+}
+
 // Programmatic dependent launch (PDL): every kernel of this library is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_grid_wait() (griddepcontrol.wait) before it
 // touches global memory, then releases its own dependents (griddepcontrol.launch_dependents).  The next kernel's

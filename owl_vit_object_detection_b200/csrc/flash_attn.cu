@@ -779,11 +779,8 @@ static int launch_fa2(const void* qkv_f16, void* ctx_f16, float* lse, int B, int
   rc = make_qkv_map(&tmKV, qkv_f16, B, S, D, KV_ROWS);
   if (rc) return rc;
   auto kern = flash_attn_fwd2_kernel<KV_ROWS, STAGES, CTAS, SPLIT, PROF, UNROLL>;
-  static bool configured = false;
-  if (!configured) {
-    OWL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    configured = true;
-  }
+  static SmemOptIn optin;   // per instantiation
+  OWL_CUDA(ensure_smem(optin, kern, Cfg::kSmem));
   const unsigned n_cta = static_cast<unsigned>((S + FA_BM - 1) / FA_BM) * H * B;
   OWL_LAUNCH(kern, n_cta, Cfg::kThreads, Cfg::kSmem, stream, tmQ, tmKV, static_cast<__half*>(ctx_f16), lse, S, D, H, sl2, prof);
   OWL_CUDA(cudaGetLastError());
@@ -865,11 +862,8 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse
   if (rc) return rc;
   rc = make_qkv_map(&tmKV, qkv_f16, B, S, D, FA_BN);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    OWL_CUDA(cudaFuncSetAttribute(flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  OWL_CUDA(ensure_smem(optin, flash_attn_fwd_kernel, FA_SMEM));
   dim3 grid((S + FA_BM - 1) / FA_BM, H, B);
   OWL_LAUNCH(flash_attn_fwd_kernel, grid, FA_THREADS, FA_SMEM, st, tmQ, tmKV, static_cast<__half*>(ctx_f16), lse, S, D,
              sl2, g_fa_dbg);

@@ -25,6 +25,11 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 
 struct Box { float x0, y0, x1, y1; };
 
+// status bits (host raises what the reference would have raised inline): 1 degenerate box (src/matcher.py:34-35),
+// 2 infeasible cost matrix, 4 num_targets outside [0, Tmax], 8 label outside [0, C) (an IndexError in the reference's
+// gather, src/matcher.py:118).  Out-of-range values are clamped so that no kernel indexes out of bounds.
+__device__ __forceinline__ int clamp_targets(int t, int Tmax) { return min(max(t, 0), Tmax); }
+
 // reference src/matcher.py:8-21 (torchvision box_area + box_iou): returns iou, writes union
 __device__ __forceinline__ float iou_union(const Box& a, const Box& b, float* uni) {
   const float area1 = fmul(fsub(a.x1, a.x0), fsub(a.y1, a.y0));
@@ -74,11 +79,17 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
 
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * COST_ROWS;
-  const int T = num_targets[b];
+  const int T = clamp_targets(num_targets[b], Tmax);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && blockIdx.x == 0 && T != num_targets[b]) atomicOr(status, 4);
 
   for (int i = threadIdx.x; i < T * 4; i += COST_THREADS) tbox[i] = tboxes[(1LL * b * Tmax) * 4 + i];
-  for (int i = threadIdx.x; i < T; i += COST_THREADS) tlab[i] = static_cast<int>(labels[1LL * b * Tmax + i]);
+  for (int i = threadIdx.x; i < T; i += COST_THREADS) {
+    const long long l = labels[1LL * b * Tmax + i];
+    const bool ok = l >= 0 && l < C;
+    if (!ok && blockIdx.x == 0) atomicOr(status, 8);
+    tlab[i] = ok ? static_cast<int>(l) : 0;
+  }
   {
     const int i = threadIdx.x;                       // 64 rows x 4 coordinates = 256 threads
     const int p = p0 + (i >> 2);
@@ -222,7 +233,7 @@ lsap_kernel(const float* __restrict__ costT, const int* __restrict__ num_targets
   short* sr_list = col4row + Tpad;
   short* sc_list = sr_list + Tpad + 4;
 
-  const int nr = num_targets[b], nc = P;
+  const int nr = clamp_targets(num_targets[b], Tmax), nc = P;
   const float* cost = costT + 1LL * b * Tmax * P;
 
   for (int j = lane; j < nc; j += 32) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
@@ -331,7 +342,7 @@ lsap_block_kernel(const float* __restrict__ costT, const int* __restrict__ num_t
   // latency (~2 scans per target, 0.6 us each).  Rows that do not fit (smem_rows) are read from global memory.
   float* scost = reinterpret_cast<float*>(lsm + lsap_block_base_bytes(P, Tmax));
 
-  const int nr = num_targets[b], nc = P;
+  const int nr = clamp_targets(num_targets[b], Tmax), nc = P;
   const float* cost = costT + 1LL * b * Tmax * P;
   const int rows_s = min(nr, smem_rows);
   if ((P & 3) == 0) {
@@ -503,7 +514,7 @@ match_loss_kernel(const float* __restrict__ sims, const float* __restrict__ boxe
   __shared__ int s_npos;
 
   const int b = blockIdx.x;
-  const int T = num_targets[b];
+  const int T = clamp_targets(num_targets[b], Tmax);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int* mp = match_pred + 1LL * b * Tmax;
 
@@ -731,13 +742,13 @@ extern "C" int owl_matcher_cost(const float* sims, const float* boxes, const lon
 #define OWL_COST_CASE(NV)                                                                                           \
   case NV:                                                                                                          \
     if (vec) {                                                                                                      \
-      static bool cfg = false;                                                                                      \
-      if (!cfg) { OWL_CUDA(cudaFuncSetAttribute(matcher_cost_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; } \
+      static SmemOptIn optin;                                                                                       \
+      OWL_CUDA(ensure_smem(optin, matcher_cost_kernel<NV, true>, 100 * 1024));                                      \
       OWL_LAUNCH((matcher_cost_kernel<NV, true>), grid, COST_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, \
                  costT, P, C, Tmax, status);                                                                        \
     } else {                                                                                                        \
-      static bool cfg = false;                                                                                      \
-      if (!cfg) { OWL_CUDA(cudaFuncSetAttribute(matcher_cost_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; } \
+      static SmemOptIn optin;                                                                                       \
+      OWL_CUDA(ensure_smem(optin, matcher_cost_kernel<NV, false>, 100 * 1024));                                     \
       OWL_LAUNCH((matcher_cost_kernel<NV, false>), grid, COST_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, \
                  costT, P, C, Tmax, status);                                                                        \
     }                                                                                                               \
@@ -770,12 +781,8 @@ extern "C" int owl_lsap(const float* costT, const int* num_targets, int B, int P
     OWL_CHECK_ARG(base1 <= 200 * 1024, "lsap: P = %d needs %zu bytes of shared memory", P, base1);
     const int smem_rows = static_cast<int>(std::min<size_t>(Tmax, (200 * 1024 - base1) / (sizeof(float) * P)));
     const size_t smem1 = base1 + sizeof(float) * P * smem_rows;
-    static size_t configured1 = 48 * 1024;
-    if (smem1 > configured1) {
-      OWL_CUDA(cudaFuncSetAttribute(lsap_block_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem1)));
-      configured1 = smem1;
-    }
+    static SmemOptIn optin1;
+    OWL_CUDA(ensure_smem(optin1, lsap_block_kernel<NT>, smem1));
     OWL_LAUNCH(lsap_block_kernel<NT>, B, NT, smem1, static_cast<cudaStream_t>(stream), costT, num_targets, P, Tmax,
                                                                                match_pred, status, smem_rows);
     OWL_CUDA(cudaGetLastError());
@@ -783,11 +790,8 @@ extern "C" int owl_lsap(const float* costT, const int* num_targets, int B, int P
   }
   const size_t smem = lsap_smem_per_warp(P, Tmax) * LSAP_WARPS;
   OWL_CHECK_ARG(smem <= 227 * 1024, "lsap: P = %d needs %zu bytes of shared memory", P, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    OWL_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  OWL_CUDA(ensure_smem(optin, lsap_kernel, smem));
   OWL_LAUNCH(lsap_kernel, (B + LSAP_WARPS - 1) / LSAP_WARPS, LSAP_WARPS * 32, smem, static_cast<cudaStream_t>(stream), 
       costT, num_targets, B, P, Tmax, match_pred, status);
   OWL_CUDA(cudaGetLastError());
@@ -807,11 +811,8 @@ extern "C" int owl_match_loss(const float* sims, const float* boxes, const long 
   const size_t smem = sizeof(float) * 4 * P + sizeof(int) * P + sizeof(float) * 8;
   OWL_CHECK_ARG(smem <= 200 * 1024, "match_loss: P = %d too large", P);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    OWL_CUDA(cudaFuncSetAttribute(match_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  OWL_CUDA(ensure_smem(optin, match_loss_kernel, smem));
   OWL_LAUNCH(match_loss_kernel, B, LOSS_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, match_pred, scales, P, C,
                                                   Tmax, bg_label, tc_matched, tc_final, pred_sorted, tgt_sorted,
                                                   losses_per_image, dsims_unit, dl1, dgiou, 1.0f / B);

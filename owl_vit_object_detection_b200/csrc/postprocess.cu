@@ -163,11 +163,8 @@ extern "C" int owl_postprocess(const float* boxes, const float* sims, int B, int
   while (pp2 < P) pp2 <<= 1;
   const size_t smem = sizeof(unsigned long long) * pp2 + (sizeof(float4) + 3 * sizeof(float)) * P + P + 16;
   OWL_CHECK_ARG(smem <= 200 * 1024, "postprocess: P = %d needs %zu bytes of shared memory", P, smem);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    OWL_CUDA(cudaFuncSetAttribute(postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  OWL_CUDA(ensure_smem(optin, postprocess_kernel, smem));
   OWL_LAUNCH(postprocess_kernel, B, PP_THREADS, smem, static_cast<cudaStream_t>(stream), boxes, sims, P, C, pp2,
              confidence_threshold, iou_threshold, out_boxes, out_classes, out_scores, out_count);
   OWL_CUDA(cudaGetLastError());

@@ -53,6 +53,7 @@ class Workspace:
         Q, C = cfg.n_queries, cfg.n_classes
         f16, f32 = torch.float16, torch.float32
         self.B = B
+        self.generation = 0                  # bumped by every Engine.forward that writes this workspace
         self.Kp = (3 * cfg.patch_size ** 2 + 7) // 8 * 8
         self.Sp = (S + 7) // 8 * 8
 
@@ -169,7 +170,8 @@ class Engine:
     def refresh_shadow(self, trainable_only: bool = False) -> None:
         """fp32 master -> fp16 GEMM operands (owl_cast_f16).  Cheap: 85 us for all of B/32, 8 us trainable."""
         lo = self.layout.train_begin if trainable_only else 0
-        ops.cast_f16(self.flat32[lo:], self.flat16[lo:])
+        with torch.cuda.device(self.device):
+            ops.cast_f16(self.flat32[lo:], self.flat16[lo:])
         if not trainable_only:
             K = 3 * self.cfg.patch_size ** 2
             w = self.p16("backbone.embeddings.patch_embedding.weight").view(self.cfg.hidden, K)
@@ -200,6 +202,10 @@ class Engine:
 
     def forward(self, image: torch.Tensor, save_for_backward: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """image [B,3,IS,IS] fp32 CUDA -> (pred_boxes [B,P,4] xyxy fp32, pred_sims [B,P,C] fp32)."""
+        with torch.cuda.device(self.device):     # kernels launch on the current device's current stream
+            return self._forward(image, save_for_backward)
+
+    def _forward(self, image: torch.Tensor, save_for_backward: bool) -> Tuple[torch.Tensor, torch.Tensor]:
         cfg, L = self.cfg, self.layout
         assert image.is_cuda and image.dtype == torch.float32 and image.dim() == 4
         assert image.shape[1] == 3 and image.shape[2] == cfg.image_size and image.shape[3] == cfg.image_size, \
@@ -210,6 +216,7 @@ class Engine:
         Q, C, eps = cfg.n_queries, cfg.n_classes, cfg.ln_eps
         self.sync_shadow()
         ws = self.workspace(B)
+        ws.generation += 1
         ops.l2_persist(ws.x)      # opt-in (OWL_L2_PERSIST=1): keep the fp32 residual stream in the L2 set-aside
         M, MP = B * S, B * P
 
@@ -281,6 +288,10 @@ class Engine:
     def backward(self, dsims: torch.Tensor, dboxes: torch.Tensor, grad_flat: torch.Tensor) -> None:
         """Accumulates d(loss)/d(trainable parameters) into grad_flat (fp32, the trainable tail of the flat
         layout), given d(loss)/d(pred_sims) [B,P,C] and d(loss)/d(pred_boxes) [B,P,4] of the LAST forward."""
+        with torch.cuda.device(self.device):
+            self._backward(dsims, dboxes, grad_flat)
+
+    def _backward(self, dsims: torch.Tensor, dboxes: torch.Tensor, grad_flat: torch.Tensor) -> None:
         cfg, L = self.cfg, self.layout
         B = dsims.shape[0]
         ws = self.workspace(B)

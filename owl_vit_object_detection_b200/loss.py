@@ -21,6 +21,7 @@ class _Buffers:
 
     def __init__(self, B: int, P: int, C: int, Tmax: int, dev):
         i64, i32, f32 = torch.int64, torch.int32, torch.float32
+        self.generation = 0                  # bumped by every HungarianMatcher.assign that writes these buffers
         self.costT = torch.zeros((B, Tmax, P), dtype=f32, device=dev)
         self.status = torch.zeros(1, dtype=i32, device=dev)
         self.match = torch.zeros((B, Tmax), dtype=i32, device=dev)
@@ -32,6 +33,18 @@ class _Buffers:
         self.dsims_unit = torch.zeros((B, P, C), dtype=f32, device=dev)
         self.dl1 = torch.zeros((B, Tmax, 4), dtype=f32, device=dev)
         self.dgiou = torch.zeros((B, Tmax, 4), dtype=f32, device=dev)
+
+
+def _raise_status(status: int) -> None:
+    """The matcher kernels flag what the reference raises inline (they cannot raise from the device)."""
+    if status & 1:
+        raise AssertionError("degenerate box: x1 < x0 or y1 < y0 (reference src/matcher.py:34-35)")
+    if status & 8:
+        raise IndexError("target label outside [0, n_classes) (reference src/matcher.py:118 gather)")
+    if status & 4:
+        raise ValueError("num_targets outside [0, Tmax]")
+    if status & 2:
+        raise ValueError("cost matrix is infeasible")
 
 
 def _pad_targets(labels, boxes, num_targets, dev) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -52,7 +65,8 @@ def _pad_targets(labels, boxes, num_targets, dev) -> Tuple[torch.Tensor, torch.T
     if lab.dim() == 1:
         lab, box = lab[None], box[None]
     if num_targets is None:
-        nt = (lab >= 0).sum(dim=1).to(torch.int32)
+        # -1 padding is trailing: the targets of an image are the labels before its first negative entry
+        nt = (lab >= 0).to(torch.int32).cumprod(dim=1).sum(dim=1).to(torch.int32)
     else:
         nt = num_targets.to(device=dev, dtype=torch.int32)
     return lab, box, nt.contiguous()
@@ -82,9 +96,11 @@ class HungarianMatcher(nn.Module):
         """Cost matrix + LSAP on the device; results stay in the returned buffers (no host sync)."""
         B, P, C = sims.shape
         buf = self.buffers(B, P, C, lab.shape[1], sims.device)
+        buf.generation += 1
         buf.status.zero_()
-        ops.matcher_cost(sims, boxes, lab, box, nt, buf.costT, buf.status)
-        ops.lsap(buf.costT, nt, buf.match, buf.status)
+        with torch.cuda.device(sims.device):
+            ops.matcher_cost(sims, boxes, lab, box, nt, buf.costT, buf.status)
+            ops.lsap(buf.costT, nt, buf.match, buf.status)
         return buf
 
     @torch.no_grad()
@@ -100,11 +116,7 @@ class HungarianMatcher(nn.Module):
                        losses_per_image=buf.losses_per_image, losses_mean4=torch.zeros(4, device=dev),
                        dsims_unit=buf.dsims_unit, dl1=buf.dl1, dgiou=buf.dgiou)
         # this entry point returns host-side index lists like the reference does, so it synchronises here
-        status = int(buf.status.item())
-        if status & 1:
-            raise AssertionError("degenerate box: x1 < x0 or y1 < y0 (reference src/matcher.py:34-35)")
-        if status & 2:
-            raise ValueError("cost matrix is infeasible")
+        _raise_status(int(buf.status.item()))
         ps, ts, ntc = buf.pred_sorted.cpu(), buf.tgt_sorted.cpu(), nt.cpu()
         indices = [(ps[b, :int(ntc[b])].clone(), ts[b, :int(ntc[b])].clone()) for b in range(B)]
         batch_idx = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
@@ -123,12 +135,16 @@ class _LossFn(torch.autograd.Function):
                        tc_matched=buf.tc_matched, tc_final=buf.tc_final, pred_sorted=buf.pred_sorted,
                        tgt_sorted=buf.tgt_sorted, losses_per_image=buf.losses_per_image, losses_mean4=losses4,
                        dsims_unit=buf.dsims_unit, dl1=buf.dl1, dgiou=buf.dgiou)
-        ctx.buf, ctx.module, ctx.shape = buf, module, (B, P, C)
+        ctx.buf, ctx.module, ctx.shape, ctx.generation = buf, module, (B, P, C), buf.generation
         return losses4
 
     @staticmethod
     def backward(ctx, g4):
         buf, module = ctx.buf, ctx.module
+        if buf.generation != ctx.generation:
+            raise RuntimeError(
+                "PushPullLoss.backward: the criterion (or its matcher) was called again with the same shapes before "
+                "this backward; the saved matcher / loss buffers were overwritten.  Call backward() first.")
         B, P, C = ctx.shape
         dev = g4.device
         dsims = torch.empty((B, P, C), dtype=torch.float32, device=dev)
@@ -162,8 +178,4 @@ class PushPullLoss(nn.Module):
         """Raises what the reference would have raised inline (degenerate boxes).  Synchronises; the train loop
         calls it where it synchronises anyway (e.g. next to `.item()` on the losses)."""
         for buf in self.matcher._buf.values():
-            status = int(buf.status.item())
-            if status & 1:
-                raise AssertionError("degenerate box: x1 < x0 or y1 < y0 (reference src/matcher.py:34-35)")
-            if status & 2:
-                raise ValueError("cost matrix is infeasible")
+            _raise_status(int(buf.status.item()))

@@ -55,13 +55,19 @@ class _Node(nn.Module):
 
 
 class _ForwardFn(torch.autograd.Function):
-    """Connects the kernel-sequenced forward / backward to autograd (reference main.py:82-90)."""
+    """Connects the kernel-sequenced forward / backward to autograd (reference main.py:82-90).
+
+    The activations the backward needs live in the engine's per-batch-size workspace, i.e. they belong to the LAST
+    forward of that batch size.  Each forward stamps a generation number; a backward whose forward is no longer
+    the latest (two forwards before one backward, an eval forward in between) raises instead of silently using
+    the wrong activations."""
 
     @staticmethod
     def forward(ctx, anchor, image, model):
         boxes, sims = model.engine.forward(image, save_for_backward=True)
         ctx.model = model
         ctx.batch = image.shape[0]
+        ctx.generation = model.engine.workspace(ctx.batch).generation
         return boxes, sims
 
     @staticmethod
@@ -70,6 +76,12 @@ class _ForwardFn(torch.autograd.Function):
         B = ctx.batch
         cfg = model.cfg
         dev = model._flat.device
+        ws = model.engine.workspace(B)
+        if ws.generation != ctx.generation:
+            raise RuntimeError(
+                "OwlViT.backward: another forward with the same batch size ran after the forward this backward "
+                "belongs to; the saved activations (one workspace per batch size) were overwritten.  Call "
+                "backward() before the next forward (reference main.py:82-90 order).")
         if dboxes is None:
             dboxes = torch.zeros((B, cfg.patches, 4), device=dev)
         if dsims is None:
@@ -186,17 +198,22 @@ class OwlViT(nn.Module):
 
     def _prepare_grads(self) -> None:
         """Make every trainable parameter's .grad a view of the flat gradient buffer.  A parameter whose .grad
-        is None (optimizer.zero_grad(set_to_none=True), reference main.py:74) gets its slice zeroed first."""
+        is None (optimizer.zero_grad(set_to_none=True), reference main.py:74) gets its slice zeroed first - per
+        parameter, so an optimizer that owns only a subset of the trainable tensors (and therefore only clears
+        that subset) still starts each of its steps from zero.  The backward kernels ACCUMULATE into the buffer."""
         g = self.flat_grad
         L = self.layout
         names = [n for n in trainable_names(self.cfg) if self._param(n).requires_grad]
-        if all(self._param(n).grad is None for n in names):
+        wholesale = all(self._param(n).grad is None for n in names)
+        if wholesale:
             g.zero_()
         for n in names:
             p = self._param(n)
             o = L.offsets[n] - L.train_begin
             view = g[o:o + L._numel(n)].view(L.shapes[n])
             if p.grad is None:
+                if not wholesale:
+                    view.zero_()
                 p.grad = view
             elif p.grad.data_ptr() != view.data_ptr():
                 raise RuntimeError(f"{n}.grad was replaced by a foreign tensor; use model.zero_grad() or "

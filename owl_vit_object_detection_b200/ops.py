@@ -224,18 +224,20 @@ def match_loss(sims, boxes, labels, tboxes, num_targets, match_pred, scales, bg_
     B, P, C = sims.shape
     assert losses_per_image.is_contiguous() and losses_per_image.numel() >= B * LOSS_WS
     Tmax = labels.shape[1]
-    check(lib().owl_match_loss(_vp(sims), _vp(boxes), _vp(labels), _vp(tboxes), _vp(num_targets), _vp(match_pred),
-                               _vp(scales), B, P, C, Tmax, bg_label, _vp(tc_matched), _vp(tc_final),
-                               _vp(pred_sorted), _vp(tgt_sorted), _vp(losses_per_image), _vp(losses_mean4),
-                               _vp(dsims_unit), _vp(dl1), _vp(dgiou), _sp()), "owl_match_loss", kernels=3)
+    with torch.cuda.device(sims.device):
+        check(lib().owl_match_loss(_vp(sims), _vp(boxes), _vp(labels), _vp(tboxes), _vp(num_targets), _vp(match_pred),
+                                   _vp(scales), B, P, C, Tmax, bg_label, _vp(tc_matched), _vp(tc_final),
+                                   _vp(pred_sorted), _vp(tgt_sorted), _vp(losses_per_image), _vp(losses_mean4),
+                                   _vp(dsims_unit), _vp(dl1), _vp(dgiou), _sp()), "owl_match_loss", kernels=3)
 
 
 def loss_backward(dsims_unit, tc_final, match_pred, dl1, dgiou, upstream4, bg_label, dsims, dboxes):
     B, P, C = dsims_unit.shape
     Tmax = match_pred.shape[1]
-    check(lib().owl_loss_backward(_vp(dsims_unit), _vp(tc_final), _vp(match_pred), _vp(dl1), _vp(dgiou),
-                                  _vp(upstream4), B, P, C, Tmax, bg_label, _vp(dsims), _vp(dboxes), _sp()),
-          "owl_loss_backward")
+    with torch.cuda.device(dsims_unit.device):
+        check(lib().owl_loss_backward(_vp(dsims_unit), _vp(tc_final), _vp(match_pred), _vp(dl1), _vp(dgiou),
+                                      _vp(upstream4), B, P, C, Tmax, bg_label, _vp(dsims), _vp(dboxes), _sp()),
+              "owl_loss_backward")
 
 
 def preprocess_workspace_bytes(H: int, W: int, out_size: int) -> int:

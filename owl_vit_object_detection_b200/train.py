@@ -34,7 +34,7 @@ class TrainStep:
                 image=torch.zeros((batch, 3, cfg.image_size, cfg.image_size), dtype=torch.float32, device=dev),
                 labels=torch.full((batch, max_targets), -1, dtype=torch.int64, device=dev),
                 boxes=torch.zeros((batch, max_targets, 4), dtype=torch.float32, device=dev),
-                nt=torch.ones((batch,), dtype=torch.int32, device=dev)))
+                nt=torch.zeros((batch,), dtype=torch.int32, device=dev)))   # no targets until load()
         self.losses = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(n_input_slots)]
         self.host_losses = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(n_input_slots)]
         self.read_done = [torch.cuda.Event() for _ in range(n_input_slots)]
@@ -50,6 +50,8 @@ class TrainStep:
         optimizer.grad_mul = 1.0 / self._world
         self._next_load = 0
         self._next_run = 0
+        self._results_read = 0
+        self.status_every = 64          # result() checks the matcher status word every this many steps (one 4-byte D2H)
 
     # ------------------------------------------------------------------ data
     def load(self, image, labels, boxes, num_targets, slot: Optional[int] = None) -> int:
@@ -119,6 +121,9 @@ class TrainStep:
     def result(self, slot: int):
         """The four losses of the last `run(slot, readback=True)` as Python floats (waits for that copy only)."""
         self.read_done[slot].synchronize()
+        self._results_read += 1
+        if self._results_read % self.status_every == 0:
+            self.criterion.check_status()       # what the reference asserts inline (degenerate boxes, bad labels)
         return self.host_losses[slot].tolist()
 
     def run(self, slot: Optional[int] = None, readback: bool = False) -> torch.Tensor:

@@ -20,15 +20,21 @@ from owl_vit_object_detection_b200 import synth  # noqa: E402
 
 
 def load_reference():
-    sys.path.insert(0, REF)
-    # the reference's modules are a top-level package called `src`, same as our drop-in mirror;
-    # make sure we import THEIRS here.
+    """Import the REFERENCE's `src` package (a namespace package: it has no __init__.py, so our own drop-in mirror
+    /root/repo/src - a regular package - would win on sys.path no matter the order).  Bind `src` to the reference
+    directory explicitly."""
+    import importlib
+    import types
     for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
         del sys.modules[k]
-    import src.models as rmodels
-    import src.losses as rlosses
-    import src.matcher as rmatcher
-    assert rmodels.__file__.startswith(REF), rmodels.__file__
+    pkg = types.ModuleType("src")
+    pkg.__path__ = [os.path.join(REF, "src")]
+    sys.modules["src"] = pkg
+    rmodels = importlib.import_module("src.models")
+    rlosses = importlib.import_module("src.losses")
+    rmatcher = importlib.import_module("src.matcher")
+    for m in (rmodels, rlosses, rmatcher):
+        assert m.__file__.startswith(REF), m.__file__
     return rmodels, rlosses, rmatcher
 
 

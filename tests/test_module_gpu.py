@@ -162,20 +162,33 @@ def test_trainstep_host_buffers_graph_matches_eager():
     assert not np.allclose(l_graph[0], l_graph[1]), "different batches must give different losses"
 
 
-@pytest.mark.xfail(strict=False, reason=(
-    "written with the last GPU seconds of round 1.  Its one run failed (98 % of the trainable elements more than 2e-5 "
-    "apart after three steps) and exposed a real defect of the torch.optim path: after Module.to() the parameters carry "
-    "version counters of their own, so the fp16 GEMM operands were not refreshed after an in-place torch.optim step.  "
-    "Fixed since (Engine.watch / Engine.version, covered on the CPU by tests/test_host_cpu.py::"
-    "test_shadow_version_tracks_parameters_after_module_to), but this test could not be re-run on a GPU before the "
-    "round ended: expected to pass, kept non-strict until it has."))
+def _per_tensor_report(model, a, b, tol):
+    """[(name, elements, elements off by more than tol, max |diff|)] over the trainable tensors of two flat parameter vectors."""
+    L = model.layout
+    rows = []
+    for n in L.trainable:
+        o, k = L.offsets[n], L._numel(n)
+        d = np.abs(a[o:o + k] - b[o:o + k])
+        rows.append((n, k, int((d > tol).sum()), float(d.max())))
+    return rows
+
+
 def test_fused_adamw_matches_torch_adamw():
     """SURVEY R14 (reference main.py:56-60,91): the fused AdamW kernel over the flat buffers against
-    torch.optim.AdamW over model.parameters() - same gradients (our backward), same hyper-parameters, three steps."""
+    torch.optim.AdamW over model.parameters() AFTER `.to("cuda")` (the reference's own construction order) - same
+    gradients (our backward), same hyper-parameters, three steps.  Strict, with a per-tensor report.
+
+    Bars: every trainable tensor within 2e-5 after three steps at lr 1e-3 (measured <= 1.5e-5: the two optimizers
+    round differently in the last bit, the next forward amplifies that through fp16 rounding of the operands).
+    `k_proj.bias` is bounded separately: its gradient is mathematically zero (softmax is invariant to a per-query
+    shift of the scores, tests/test_backward_gpu.py docstring), so what reaches Adam is rounding noise whose SIGN
+    decides a full +-lr step; the reference's autograd has the same property.  It must stay within the 3 * lr an
+    Adam step sequence can move a weight (+ weight decay), nothing tighter is meaningful.
+    Also asserted: the fp16 GEMM operands equal the fp32 parameters at every forward (no stale shadow)."""
     from src.losses import PushPullLoss
     from src.models import FusedAdamW
     cfg = synth.TINY
-    B = 2
+    B, lr, steps = 2, 1e-3, 3
     img = synth.make_images(cfg, B, seed=15).cuda()
     labels, tboxes, nt = [x.cuda() for x in synth.make_targets(cfg, B, seed=13, max_t=8)]
     scales = synth.make_class_scales(cfg).cuda()
@@ -183,27 +196,156 @@ def test_fused_adamw_matches_torch_adamw():
     def run(fused):
         model, _ = _model(cfg)
         crit = PushPullLoss(cfg.n_classes, scales)
-        opt = (FusedAdamW(model, lr=1e-3, weight_decay=0.1) if fused
-               else torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.1))
+        opt = (FusedAdamW(model, lr=lr, weight_decay=0.1) if fused
+               else torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=0.1))
         start = model.flat_params.detach().clone()
-        for _ in range(3):
+        lo = model.layout.train_begin
+        for _ in range(steps):
             if fused:
                 opt.zero_grad(set_to_none=False)
             else:
                 opt.zero_grad()
             boxes, _, sims, _ = model(img)
+            stale = int((model.engine.flat16[lo:] != model.flat_params[lo:].half()).sum().item())
+            assert stale == 0, f"{stale} fp16 GEMM operand elements do not follow the fp32 parameters"
             l = crit(sims, labels, boxes, tboxes, num_targets=nt)
             (l["loss_ce"] + l["loss_bg"] + l["loss_bbox"] + l["loss_giou"]).backward()
             opt.step()
         torch.cuda.synchronize()
-        return start.cpu().numpy(), model.flat_params.detach().cpu().numpy().copy()
+        return model, start.cpu().numpy(), model.flat_params.detach().cpu().numpy().copy()
 
-    s0, p_fused = run(True)
-    s1, p_torch = run(False)
+    model, s0, p_fused = run(True)
+    _, s1, p_torch = run(False)
     assert np.array_equal(s0, s1)
     moved = np.abs(p_torch - s1).max()
     assert moved > 1e-3, "three steps at lr 1e-3 must move the trainable parameters"
-    # gradients of consecutive steps differ in the last bits (atomics order), the optimizers themselves agree to fp32
-    np.testing.assert_allclose(p_fused, p_torch, rtol=0, atol=2e-5)
+    bad = []
+    for name, k, n_off, mx in _per_tensor_report(model, p_fused, p_torch, 2e-5):
+        print(f"  {name:58s} n={k:7d} off={n_off:6d} max|diff|={mx:.3e}")
+        if name.endswith("k_proj.bias"):
+            if mx > 2 * steps * lr * 1.1:
+                bad.append((name, n_off, mx))
+        elif n_off:
+            bad.append((name, n_off, mx))
+    assert not bad, bad
     frozen = np.abs(p_torch - s1) == 0
     assert np.array_equal(p_fused[frozen], s1[frozen]), "frozen parameters must not move"
+
+
+def test_main_replay_three_steps_vs_reference_golden(golden_dir):
+    """reference main.py:42-91 replayed literally on B/32: `OwlViT(...).to("cuda")`, `torch.optim.AdamW(
+    model.parameters(), lr, weight_decay)`, then three times zero_grad / forward / PushPullLoss / backward / step
+    (batch 1, images 0, 1, 0) - against tests/golden/train3_b32.npz, produced by the REAL reference doing the same
+    three CPU fp32 steps (tests/golden/make_golden_train3.py).
+
+    Bars (fp16 operands against an fp32 reference, through Adam):
+      * the four losses of every step within 2e-2 relative.  Step 2 revisits image 0 after two updates: the golden
+        loss_ce falls 25.0 -> 20.6, so a forward that kept reading stale fp16 weights fails here by 20 %;
+      * per trainable tensor, the displacement p_3 - p_0: Adam's update is lr * m / (sqrt(v) + eps) ~ lr * sign(g)
+        for the first steps, so an element whose gradient is small against the fp16 forward noise can legitimately
+        differ by a whole step.  Stated bars: cosine(displacement, golden) >= 0.98, norm within 3 %, mean |diff| <=
+        0.04 * (3 lr) and no element further than 2 * 3 lr (measured values are printed).  `k_proj.bias` (zero
+        gradient, pure noise, see test_fused_adamw_matches_torch_adamw) only has to stay inside 3 lr (1 + wd).
+      * after every optimizer step the fp16 GEMM operands equal the fp32 parameters."""
+    import os
+    from src.losses import PushPullLoss
+    gold = np.load(os.path.join(golden_dir, "train3_b32.npz"))
+    lr, wd, steps = float(gold["lr"]), float(gold["weight_decay"]), int(gold["steps"])
+    cfg = synth.B32
+    model, _ = _model(cfg, seed=0)                                  # OwlViT(...).to("cuda")
+    L = model.layout
+    start = {n: model._param(n).detach().clone() for n in L.trainable}
+    crit = PushPullLoss(cfg.n_classes, synth.make_class_scales(cfg).cuda())
+    opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd)
+    image = synth.make_images(cfg, 2, seed=2).cuda()
+    labels, tboxes, nt = synth.make_targets(cfg, 2, seed=3)
+    model.train()
+    lo = L.train_begin
+    for step in range(steps):
+        b = step % 2
+        t = int(nt[b])
+        opt.zero_grad()
+        boxes, _, sims, _ = model(image[b:b + 1])
+        assert torch.equal(model.engine.flat16[lo:], model.flat_params[lo:].half()), "stale fp16 GEMM operands"
+        losses = crit(sims, labels[b:b + 1, :t].cuda(), boxes, tboxes[b:b + 1, :t].cuda())
+        (losses["loss_ce"] + losses["loss_bg"] + losses["loss_bbox"] + losses["loss_giou"]).backward()
+        opt.step()
+        for k in ("loss_ce", "loss_bg", "loss_bbox", "loss_giou"):
+            np.testing.assert_allclose(losses[k].item(), float(gold[f"{k}{step}"]), rtol=2e-2, err_msg=f"{k} step {step}")
+    crit.check_status()
+    bad = []
+    for n in L.trainable:
+        d = synth.subsample((model._param(n).detach() - start[n]).cpu()).numpy().astype(np.float64).ravel()
+        r = gold["disp." + n].astype(np.float64).ravel()
+        diff = np.abs(d - r)
+        if n.endswith("k_proj.bias"):
+            ok = np.abs(d).max() <= steps * lr * (1 + wd) * 1.05
+            print(f"  {n:58s} max|disp| {np.abs(d).max():.3e} (noise gradient: bounded only)")
+        else:
+            cos = float(d @ r / (np.linalg.norm(d) * np.linalg.norm(r) + 1e-30))
+            full_norm = float((model._param(n).detach() - start[n]).norm().item())
+            nrel = abs(full_norm - float(gold["dispnorm." + n])) / float(gold["dispnorm." + n])
+            mean_rel, mx_rel = diff.mean() / (steps * lr), diff.max() / (steps * lr)
+            ok = cos >= 0.98 and nrel <= 3e-2 and mean_rel <= 0.04 and mx_rel <= 2.0
+            print(f"  {n:58s} cos {cos:.5f} norm rel {nrel:.2e} mean|diff|/(3lr) {mean_rel:.3e} max {mx_rel:.3e}")
+        if not ok:
+            bad.append(n)
+    assert not bad, bad
+
+
+def test_subset_optimizer_grads_do_not_accumulate():
+    """An optimizer that owns only the heads clears only their .grad (set_to_none): every step must still start
+    those gradients from zero, although the backward kernels accumulate into the flat buffer."""
+    from src.losses import PushPullLoss
+    cfg = synth.TINY
+    model, _ = _model(cfg)
+    crit = PushPullLoss(cfg.n_classes, synth.make_class_scales(cfg).cuda())
+    heads = [p for n, p in model.named_parameters() if p.requires_grad and n.startswith("box_head")]
+    opt = torch.optim.SGD(heads, lr=0.0)
+    img = synth.make_images(cfg, 1, seed=5).cuda()
+    labels, tboxes, nt = [x.cuda() for x in synth.make_targets(cfg, 1, seed=3, max_t=8)]
+    grads = []
+    for _ in range(2):
+        opt.zero_grad()                           # clears the heads only
+        boxes, _, sims, _ = model(img)
+        l = crit(sims, labels, boxes, tboxes, num_targets=nt)
+        (l["loss_ce"] + l["loss_bg"] + l["loss_bbox"] + l["loss_giou"]).backward()
+        grads.append((model._param("box_head.dense0.weight").grad.clone(),
+                      model._param("class_predictor.dense0.weight").grad.clone()))
+    np.testing.assert_allclose(grads[1][0].cpu().numpy(), grads[0][0].cpu().numpy(), rtol=1e-4, atol=1e-7)
+    # parameters nobody cleared keep accumulating (torch semantics)
+    np.testing.assert_allclose(grads[1][1].cpu().numpy(), 2 * grads[0][1].cpu().numpy(), rtol=1e-3, atol=1e-7)
+
+
+def test_backward_of_an_overwritten_forward_raises():
+    """Saved activations live in one workspace per batch size: a backward whose forward is no longer the latest must
+    raise instead of using the wrong activations; same for the criterion's buffers."""
+    from src.losses import PushPullLoss
+    cfg = synth.TINY
+    model, _ = _model(cfg)
+    crit = PushPullLoss(cfg.n_classes, None)
+    img = synth.make_images(cfg, 1, seed=5).cuda()
+    labels, tboxes, nt = [x.cuda() for x in synth.make_targets(cfg, 1, seed=3, max_t=8)]
+    boxes, _, sims, _ = model(img)
+    model(img)                                    # second forward, same batch size
+    with pytest.raises(RuntimeError, match="another forward"):
+        (sims.sum() + boxes.sum()).backward()
+    boxes, _, sims, _ = model(img)
+    l = crit(sims, labels, boxes, tboxes, num_targets=nt)
+    crit(sims.detach(), labels, boxes.detach(), tboxes, num_targets=nt)
+    with pytest.raises(RuntimeError, match="called again"):
+        l["loss_ce"].backward()
+
+
+def test_matcher_flags_out_of_range_labels_and_counts():
+    """reference src/matcher.py:118 raises IndexError on a label >= n_classes; the kernels clamp and flag."""
+    from src.matcher import HungarianMatcher
+    g = torch.Generator().manual_seed(0)
+    sims = (torch.rand((1, 64, 8), generator=g) * 0.4 - 0.1).cuda()
+    xy = torch.rand((1, 64, 2), generator=g) * 0.5
+    boxes = torch.cat([xy, xy + 0.1 + 0.3 * torch.rand((1, 64, 2), generator=g)], dim=-1).cuda()
+    tb = torch.tensor([[0.1, 0.1, 0.4, 0.5], [0.3, 0.2, 0.9, 0.8]]).cuda()
+    m = HungarianMatcher(8)
+    m({"pred_logits": sims, "pred_boxes": boxes}, [{"labels": torch.tensor([1, 7]).cuda(), "boxes": tb}])
+    with pytest.raises(IndexError):
+        m({"pred_logits": sims, "pred_boxes": boxes}, [{"labels": torch.tensor([1, 8]).cuda(), "boxes": tb}])
