@@ -95,6 +95,12 @@ int owl_gemm(const owl_gemm_args* args, void* stream);
 /* HF:336 patch-embedding conv (kernel = stride = patch, no bias) as a gather: img [B,3,IS,IS] f32 NCHW ->
  * patches [B*(IS/patch)^2, ld] fp16 with column = c*patch^2 + ky*patch + kx (the conv weight's own order). */
 int owl_im2col_f16(const float* img, void* patches, int B, int image_size, int patch, long long ld, void* stream);
+/* reference src/dataset.py:64-71 (HF OwlViTImageProcessor: /255, CLIP mean / std) + HF:336 patch gather in ONE pass for
+ * images that already have the model's resolution (PIL's resize is then the identity): img [B,IS,IS,3] uint8 RGB (HWC)
+ * -> patches [B*(IS/patch)^2, ld] fp16, lut [3][256] fp32 = normalised value of byte v in channel c.  Bit-identical to
+ * owl_preprocess_image + owl_im2col_f16 on such images; the host ships 1 byte per channel instead of 4. */
+int owl_u8_patches_f16(const unsigned char* img, const float* lut, void* patches, int B, int image_size, int patch,
+                       long long ld, void* stream);
 /* HF:498,507,768 + reference src/models.py:80,86 LayerNorm over rows of length D (fp32 in; fp16 or fp32 out).
  * Row r is read at x + r*x_stride and written at y + r*y_stride.  When cls_emb != NULL, rows with
  * r %% tokens == 0 are replaced by cls_emb + pos0 first (the CLS row of the embedding, HF:338-343). */

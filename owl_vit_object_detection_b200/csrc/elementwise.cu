@@ -66,6 +66,48 @@ __global__ void im2col_kernel(const float* __restrict__ img, __half* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ raw pixels -> patch rows (one pass)
+// img [B,IS,IS,3] uint8 RGB (HWC, as decoded) -> patches [B*g*g, ld] fp16, same column order as im2col_kernel.
+// lut [3][256] fp32 = the value byte v of channel c takes after the reference's rescale (/255) + CLIP normalise
+// (src/dataset.py:64-71 -> HF OwlViTImageProcessor; built on the host, preprocess.py).  For an image that already
+// has the model's resolution PIL's resize is the identity, so this kernel alone is the whole reference
+// preprocessing followed by the fp16 cast of im2col_kernel: bit-identical patches from a quarter of the bytes.
+// One thread = 8 consecutive pixels of a row: 24 contiguous bytes in, three 16-byte stores out (one per channel).
+__global__ void u8_patches_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut,
+                                  __half* __restrict__ out, int B, int IS, int ps, int ld) {
+  __shared__ float slut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) slut[i] = lut[i];
+  pdl_grid_wait();
+  __syncthreads();
+  const int g = IS / ps;
+  const int groups_per_row = IS / 8;
+  const long long total = 1LL * B * IS * groups_per_row;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int xg = static_cast<int>(i % groups_per_row);
+    long long r = i / groups_per_row;
+    const int y = static_cast<int>(r % IS);
+    const int b = static_cast<int>(r / IS);
+    const int x = xg * 8;
+    const uint2* src = reinterpret_cast<const uint2*>(img + ((1LL * b * IS + y) * IS + x) * 3);   // 24 B, 8-aligned
+    const uint2 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    const uint32_t w[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+    const int py = y / ps, ky = y - py * ps, px = x / ps, kx = x - px * ps;
+    __half* dst = out + (1LL * b * g * g + py * g + px) * ld + ky * ps + kx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t hh[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i0 = (2 * k) * 3 + c, i1 = (2 * k + 1) * 3 + c;          // byte index inside the 24
+        const uint32_t v0 = (w[i0 >> 2] >> ((i0 & 3) * 8)) & 0xffu, v1 = (w[i1 >> 2] >> ((i1 & 3) * 8)) & 0xffu;
+        const __half2 h = __floats2half2_rn(slut[c * 256 + v0], slut[c * 256 + v1]);
+        hh[k] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(dst + 1LL * c * ps * ps) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm (HF:498,507,768; eps 1e-5)
 // y[r] = LN(x[r]) * gamma + beta.  Row r is read at x + r * x_stride (so a strided subset of rows, e.g.
 // the CLS rows, can be normalised).  If `cls_emb` is set, rows with r % tokens == 0 take their input
@@ -327,6 +369,19 @@ extern "C" int owl_im2col_f16(const float* img, void* out, int B, int image_size
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
   if (v8) OWL_LAUNCH(im2col_kernel<8>, blocks, 256, 0, s, img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
   else OWL_LAUNCH(im2col_kernel<2>, blocks, 256, 0, s, img, static_cast<__half*>(out), B, image_size, patch, (int)ld);
+  OWL_CUDA(cudaGetLastError());
+  return OWL_OK;
+}
+
+extern "C" int owl_u8_patches_f16(const unsigned char* img, const float* lut, void* out, int B, int image_size,
+                                  int patch, long long ld, void* stream) {
+  OWL_CHECK_ARG(img && lut && out && B > 0 && patch > 0 && image_size % patch == 0, "u8_patches: bad arguments");
+  OWL_CHECK_ARG(patch % 8 == 0 && ld % 8 == 0, "u8_patches: patch %% 8 and ld %% 8 must be 0 (patch %d, ld %lld)", patch, ld);
+  OWL_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 7) == 0, "u8_patches: img must be 8-byte aligned");
+  const long long total = 1LL * B * image_size * (image_size / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  OWL_LAUNCH(u8_patches_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), img, lut, static_cast<__half*>(out), B,
+             image_size, patch, static_cast<int>(ld));
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

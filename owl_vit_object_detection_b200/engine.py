@@ -146,6 +146,7 @@ class Engine:
         self._ws: Dict[int, Workspace] = {}
         self._watch: list = []          # tensors aliasing flat32 that carry version counters of their own (watch())
         self._shadow_version = None
+        self._lut: Optional[torch.Tensor] = None
         self.refresh_shadow()
 
     def watch(self, tensors) -> None:
@@ -185,6 +186,14 @@ class Engine:
         if self.version() != self._shadow_version:
             self.refresh_shadow()
 
+    def pixel_lut(self) -> torch.Tensor:
+        """[3, 256] fp32: rescale (/255) + CLIP normalise of a raw byte, as the reference's processor does it
+        (reference src/dataset.py:64-71; built by preprocess.rescale_normalize_lut)."""
+        if self._lut is None:
+            from .preprocess import rescale_normalize_lut
+            self._lut = torch.from_numpy(rescale_normalize_lut()).to(self.device).contiguous()
+        return self._lut
+
     def workspace(self, B: int) -> Workspace:
         ws = self._ws.get(B)
         if ws is None:
@@ -207,9 +216,16 @@ class Engine:
 
     def _forward(self, image: torch.Tensor, save_for_backward: bool) -> Tuple[torch.Tensor, torch.Tensor]:
         cfg, L = self.cfg, self.layout
-        assert image.is_cuda and image.dtype == torch.float32 and image.dim() == 4
-        assert image.shape[1] == 3 and image.shape[2] == cfg.image_size and image.shape[3] == cfg.image_size, \
-            f"expected [B,3,{cfg.image_size},{cfg.image_size}], got {tuple(image.shape)}"
+        assert image.is_cuda and image.dim() == 4
+        raw = image.dtype == torch.uint8      # raw RGB bytes [B,IS,IS,3] at the model's resolution (see ops.u8_patches_f16)
+        if raw:
+            assert image.shape[1] == cfg.image_size and image.shape[2] == cfg.image_size and image.shape[3] == 3, \
+                f"expected uint8 [B,{cfg.image_size},{cfg.image_size},3], got {tuple(image.shape)}"
+            assert cfg.patch_size % 8 == 0, "the raw-pixel path needs a patch size that is a multiple of 8"
+        else:
+            assert image.dtype == torch.float32
+            assert image.shape[1] == 3 and image.shape[2] == cfg.image_size and image.shape[3] == cfg.image_size, \
+                f"expected [B,3,{cfg.image_size},{cfg.image_size}], got {tuple(image.shape)}"
         image = image.contiguous()
         B = image.shape[0]
         S, P, D, F, E = cfg.tokens, cfg.patches, cfg.hidden, cfg.ff, cfg.embed
@@ -221,7 +237,10 @@ class Engine:
         M, MP = B * S, B * P
 
         # ---- embeddings HF:334-344 + pre_layernorm HF:768
-        ops.im2col_f16(image, ws.patches16, cfg.patch_size)
+        if raw:
+            ops.u8_patches_f16(image, self.pixel_lut(), ws.patches16, cfg.patch_size)
+        else:
+            ops.im2col_f16(image, ws.patches16, cfg.patch_size)
         ops.gemm(ws.patches16, self.patch_w16, ws.emb, M=MP, N=D, K=ws.Kp,
                  pos=self.p32("backbone.embeddings.position_embedding.weight"), rows_per_img=P)
         ops.layernorm(ws.emb, self.p32("backbone.pre_layernorm.weight"), self.p32("backbone.pre_layernorm.bias"),

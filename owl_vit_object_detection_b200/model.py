@@ -243,18 +243,23 @@ class OwlViT(nn.Module):
             # raw RGB pixels [B,H,W,3]: the reference's CPU preprocessing (src/dataset.py:64-71) runs on the device
             if image.shape[3] != 3:
                 raise ValueError(f"uint8 input must be raw RGB [B,H,W,3], got {tuple(image.shape)}")
-            if self._pre is None:
-                from .preprocess import DevicePreprocessor
-                self._pre = DevicePreprocessor(self.cfg.image_size, self._flat.device)
-            image = self._pre(list(image))
+            IS = self.cfg.image_size
+            if image.shape[1] == IS and image.shape[2] == IS and self.cfg.patch_size % 8 == 0:
+                pass    # already at the model's resolution: normalised inside the patch gather (owl_u8_patches_f16)
+            else:
+                if self._pre is None:
+                    from .preprocess import DevicePreprocessor
+                    self._pre = DevicePreprocessor(IS, self._flat.device)
+                image = self._pre(list(image))
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             self._check_policy()
             if self._anchor is None:
                 self._anchor = torch.zeros(1, device=self._flat.device, requires_grad=True)
-            boxes, sims = _ForwardFn.apply(self._anchor, image.float(), self)
+            boxes, sims = _ForwardFn.apply(self._anchor, image if image.dtype == torch.uint8 else image.float(), self)
         else:
-            boxes, sims = self.engine.forward(image.float(), save_for_backward=False)
+            boxes, sims = self.engine.forward(image if image.dtype == torch.uint8 else image.float(),
+                                              save_for_backward=False)
         return boxes, None, sims, None
 
 

@@ -95,6 +95,18 @@ def im2col_f16(img: torch.Tensor, patches: torch.Tensor, patch: int) -> torch.Te
     return patches
 
 
+def u8_patches_f16(img_u8: torch.Tensor, lut: torch.Tensor, patches: torch.Tensor, patch: int) -> torch.Tensor:
+    """Raw RGB uint8 [B,IS,IS,3] at the model's resolution -> normalised fp16 patch rows (owl_u8_patches_f16)."""
+    assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3
+    assert img_u8.is_contiguous() and img_u8.shape[1] == img_u8.shape[2]
+    _f32(lut)
+    assert lut.numel() == 768 and patches.dtype == torch.float16 and patches.is_cuda
+    B, IS = int(img_u8.shape[0]), int(img_u8.shape[1])
+    check(lib().owl_u8_patches_f16(_vp(img_u8), _vp(lut), _vp(patches), B, IS, patch,
+                                   ctypes.c_longlong(patches.stride(0)), _sp()), "owl_u8_patches_f16")
+    return patches
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, *, rows: int, D: int,
               eps: float, x_stride: Optional[int] = None, y_stride: Optional[int] = None,
               cls_emb: Optional[torch.Tensor] = None, pos0: Optional[torch.Tensor] = None,

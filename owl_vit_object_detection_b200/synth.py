@@ -148,6 +148,13 @@ def make_images(cfg: OwlConfig, batch: int, seed: int = 2) -> torch.Tensor:
     return x.clamp_(-1.8, 2.2)
 
 
+def make_images_u8(cfg: OwlConfig, batch: int, seed: int = 2) -> torch.Tensor:
+    """Raw RGB bytes [B, IS, IS, 3] (HWC, what an image decoder yields) at the model's resolution: the input of the
+    device-side preprocessing path (reference src/dataset.py:64-71 does rescale + normalise on the CPU instead)."""
+    g = _gen(seed, "images_u8")
+    return torch.randint(0, 256, (batch, cfg.image_size, cfg.image_size, 3), generator=g, dtype=torch.uint8)
+
+
 def make_targets(cfg: OwlConfig, batch: int, seed: int = 3, fixed_t: int | None = None,
                  max_t: int = 100) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """COCO-shaped targets.  Returns (labels [B,max_t] i64, boxes [B,max_t,4] f32 rel-xyxy,

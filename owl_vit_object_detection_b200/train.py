@@ -23,7 +23,11 @@ from .model import FusedAdamW, OwlViT
 
 class TrainStep:
     def __init__(self, model: OwlViT, criterion: PushPullLoss, optimizer: FusedAdamW, batch: int,
-                 max_targets: int = 100, use_graph: bool = True, n_input_slots: int = 2, group=None):
+                 max_targets: int = 100, use_graph: bool = True, n_input_slots: int = 2, group=None,
+                 raw_u8: bool = False):
+        """raw_u8: the input slots hold raw RGB bytes [B,IS,IS,3] (what a decoder produces; the reference's CPU
+        rescale + normalise, src/dataset.py:64-71, then happens inside the patch gather on the device) instead of
+        the reference's fp32 `pixel_values` [B,3,IS,IS]: a quarter of the host-to-device bytes per step."""
         cfg = model.cfg
         dev = model.flat_params.device
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
@@ -31,7 +35,8 @@ class TrainStep:
         self.slots = []
         for _ in range(n_input_slots):
             self.slots.append(dict(
-                image=torch.zeros((batch, 3, cfg.image_size, cfg.image_size), dtype=torch.float32, device=dev),
+                image=(torch.zeros((batch, cfg.image_size, cfg.image_size, 3), dtype=torch.uint8, device=dev) if raw_u8
+                       else torch.zeros((batch, 3, cfg.image_size, cfg.image_size), dtype=torch.float32, device=dev)),
                 labels=torch.full((batch, max_targets), -1, dtype=torch.int64, device=dev),
                 boxes=torch.zeros((batch, max_targets, 4), dtype=torch.float32, device=dev),
                 nt=torch.zeros((batch,), dtype=torch.int32, device=dev)))   # no targets until load()
@@ -117,6 +122,13 @@ class TrainStep:
         self.optimizer.exp_avg_sq.copy_(state[2])
         self.optimizer.state.copy_(state[3])
         self.model.engine.refresh_shadow()
+
+    def launch_description(self) -> str:
+        if not self.use_graph:
+            return "eager launches"
+        if self._world == 1:
+            return "one CUDA-graph replay per step (fwd + loss + bwd + AdamW)"
+        return "two CUDA-graph replays per step (fwd+loss+bwd, AdamW) around the NCCL all-reduce"
 
     def result(self, slot: int):
         """The four losses of the last `run(slot, readback=True)` as Python floats (waits for that copy only)."""

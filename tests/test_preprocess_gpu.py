@@ -38,3 +38,29 @@ def test_forward_accepts_raw_uint8():
         b0, _, s0, _ = model(raw)
         b1, _, s1, _ = model(DevicePreprocessor(cfg.image_size)(list(raw)))
     assert torch.equal(b0, b1) and torch.equal(s0, s1)
+
+
+def test_raw_uint8_at_model_resolution_is_one_fused_pass_and_bit_equal():
+    """Images that already have the model's resolution skip the resample (PIL's resize is the identity there) and are
+    normalised inside the patch gather (owl_u8_patches_f16).  The patch rows must equal, bit for bit, what the
+    reference's preprocessing (oracle: preprocess_oracle.preprocess, pinned to real PIL fixtures) followed by the fp32
+    path's im2col produces - and so must the model outputs."""
+    from owl_vit_object_detection_b200 import ops
+    from owl_vit_object_detection_b200.model import OwlViT
+    cfg = synth.TINY
+    IS, ps = cfg.image_size, cfg.patch_size
+    raw_np = np.stack([synth.make_raw_image(IS, IS, seed=10 + s) for s in range(3)])
+    raw = torch.from_numpy(raw_np).cuda()
+    ref32 = torch.from_numpy(np.stack([pre.preprocess(im, IS) for im in raw_np])).cuda()      # [B,3,IS,IS] fp32
+    sd = synth.make_weights(cfg, seed=0)
+    model = OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg, device="cuda")
+    K = 3 * ps * ps
+    pa = torch.zeros((3 * cfg.patches, K), dtype=torch.float16, device="cuda")
+    pb = torch.zeros_like(pa)
+    ops.u8_patches_f16(raw, model.engine.pixel_lut(), pa, ps)
+    ops.im2col_f16(ref32, pb, ps)
+    assert torch.equal(pa, pb)
+    with torch.no_grad():
+        b0, _, s0, _ = model(raw)
+        b1, _, s1, _ = model(ref32)
+    assert torch.equal(b0, b1) and torch.equal(s0, s1)
