@@ -6,7 +6,7 @@ the three modules of the hot path,
 
     /root/reference/src/models.py   /root/reference/src/matcher.py   /root/reference/src/losses.py
 
-into sourceless `.pyc` files under `oracle/_ref/src/` (`install()`, called by `__graft_entry__.build()` when
+into sourceless byte-code files (`*.refbin`, the `.pyc` format) under `oracle/_ref/src/` (`install()`, called by `__graft_entry__.build()` when
 /root/reference is present).  `oracle/_ref/` is git-ignored (no reference source or binary enters the history) but not
 gpurun-ignored, so the compiled modules travel to the GPU box like our own built `.so`; the box has the same image,
 hence the same interpreter and the same third-party packages the reference imports (torch, transformers, scipy,
@@ -31,28 +31,30 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src"
 COMPILED = os.path.join(_HERE, "_ref", "src")
 MODULES = ("matcher", "losses", "models")        # import order: losses imports matcher
+EXT = ".refbin"                                  # CPython byte-code (.pyc format); not named *.pyc so that no
+                                                 # "ignore compiled python" rule of a sync tool drops it on the way
 _PKG = "_owl_reference_src"                      # private package name: never collides with our own `src` mirror
 _loaded = None
 
 
 def install(verbose: bool = False) -> bool:
-    """Byte-compile the reference's hot-path modules into oracle/_ref/src/*.pyc.  No-op without /root/reference."""
+    """Byte-compile the reference's hot-path modules into oracle/_ref/src/*.refbin.  No-op without /root/reference."""
     if not os.path.isdir(REF_SRC):
         return False
     os.makedirs(COMPILED, exist_ok=True)
     for m in MODULES:
-        py_compile.compile(os.path.join(REF_SRC, m + ".py"), cfile=os.path.join(COMPILED, m + ".pyc"),
+        py_compile.compile(os.path.join(REF_SRC, m + ".py"), cfile=os.path.join(COMPILED, m + EXT),
                            dfile=f"reference/src/{m}.py", doraise=True)
         if verbose:
-            print(f"oracle/_ref/src/{m}.pyc <- {REF_SRC}/{m}.py")
+            print(f"oracle/_ref/src/{m}{EXT} <- {REF_SRC}/{m}.py")
     return True
 
 
 def _where() -> Optional[Tuple[str, str]]:
     if os.path.isdir(REF_SRC) and all(os.path.exists(os.path.join(REF_SRC, m + ".py")) for m in MODULES):
         return REF_SRC, ".py"
-    if all(os.path.exists(os.path.join(COMPILED, m + ".pyc")) for m in MODULES):
-        return COMPILED, ".pyc"
+    if all(os.path.exists(os.path.join(COMPILED, m + EXT)) for m in MODULES):
+        return COMPILED, EXT
     return None
 
 
@@ -69,7 +71,7 @@ def load():
         return _loaded
     w = _where()
     if w is None:
-        raise RuntimeError("the reference is not available: neither /root/reference/src nor oracle/_ref/src/*.pyc")
+        raise RuntimeError("the reference is not available: neither /root/reference/src nor oracle/_ref/src/*.refbin")
     folder, ext = w
     saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
     for k in saved:
@@ -112,7 +114,8 @@ def build_model(cfg, sd, attn_implementation: str = "eager"):
     hf_cfg = OwlViTConfig(vision_config=vc, text_config=dict(hidden_size=cfg.embed), projection_dim=cfg.embed)
     hf = OwlViTForObjectDetection._from_config(hf_cfg, attn_implementation=attn_implementation)
     orig = hf.compute_box_bias
-    hf.compute_box_bias = lambda fm: orig(fm.shape[1], fm.shape[2])          # D7 shim
+    # D7 shim: 4.30.2's `compute_box_bias(feature_map)` built the same [P, 4] constant and moved it to feature_map.device
+    hf.compute_box_bias = lambda fm: orig(fm.shape[1], fm.shape[2]).to(fm.device)
     model = rmodels.OwlViT(hf, sd["queries"].clone())
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected

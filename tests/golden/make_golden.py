@@ -43,7 +43,7 @@ def build_reference_model(rmodels, cfg, sd):
     assert cfg == synth.B32
     hf = OwlViTForObjectDetection._from_config(OwlViTConfig(), attn_implementation="eager")
     orig = hf.compute_box_bias
-    hf.compute_box_bias = lambda fm: orig(fm.shape[1], fm.shape[2])          # D7 shim
+    hf.compute_box_bias = lambda fm: orig(fm.shape[1], fm.shape[2]).to(fm.device)      # D7 shim
     model = rmodels.OwlViT(hf, sd["queries"].clone())
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
