@@ -504,27 +504,50 @@ def _torch_cuda_port(B, cfg, sd, imgs, labels, tboxes, nt, scales):
 
 
 # ====================================================================================== our arm
-def time_kernel(fn, flush, pre=None, reps=20):
-    """Average device time of one launch (ms), under the cache conditions the launch meets inside the step: before
-    every timed launch L2 is flushed (a 256 MB memset) and then `pre` - the kernel that PRODUCES the timed kernel's
-    input activations in the step - runs, so activations are as L2-warm as the producer leaves them and weights come
-    from HBM.  CUDA events around each single launch, on the launching stream."""
+def time_layer_kernels(eng, ws, cfg, B, reps=4):
+    """Average device time (ms) of each kernel of an encoder layer (HF:490-511) under the conditions it meets inside the
+    step: the twelve layers are swept in order with their own weights, exactly as Engine.forward launches them, so
+    every launch finds activations as L2-warm as its producer left them and weights as cold as in the step; CUDA
+    events on the launching stream around every single launch (the queue stays full, so an interval is kernel
+    duration + the ~1 us hand-over, never host latency).  The first sweep is a warm-up."""
     import torch
-    for _ in range(3):
-        if pre is not None:
-            pre()
-        fn()
-    torch.cuda.synchronize()
-    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for e0, e1 in pairs:
-        flush.zero_()
-        if pre is not None:
-            pre()
-        e0.record()
-        fn()
-        e1.record()
-    torch.cuda.synchronize()
-    return sum(e0.elapsed_time(e1) for e0, e1 in pairs) / reps
+    from owl_vit_object_detection_b200 import ops
+    S, D, F, H, dh, eps = cfg.tokens, cfg.hidden, cfg.ff, cfg.heads, cfg.head_dim, cfg.ln_eps
+    M = B * S
+    L = eng.layout
+    names = ("ln1", "qkv", "attn", "out_proj", "ln2", "fc1", "fc2")
+    acc = {n: [] for n in names}
+    x0 = ws.x.clone()          # a real residual-stream state (input of the last layer of the last step)
+    for rep in range(reps + 1):
+        ws.x.copy_(x0)
+        evs = []
+        for i in range(cfg.layers):
+            p = f"backbone.encoder.layers.{i}."
+            lo, hi = L.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight")
+            wqkv = eng.flat16[lo:hi].view(3 * D, D)
+            lo, hi = L.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias")
+            bqkv = eng.flat32[lo:hi]
+            seq = (
+                ("ln1", lambda: ops.layernorm(ws.x, eng.p32(p + "layer_norm1.weight"), eng.p32(p + "layer_norm1.bias"), ws.h1, rows=M, D=D, eps=eps)),
+                ("qkv", lambda: ops.gemm(ws.h1, wqkv, ws.qkv, M=M, N=3 * D, K=D, bias=bqkv)),
+                ("attn", lambda: ops.flash_attn_fwd(ws.qkv, ws.ctx, B=B, S=S, H=H, head_dim=dh, scale=dh ** -0.5)),
+                ("out_proj", lambda: ops.gemm(ws.ctx, eng.p16(p + "self_attn.out_proj.weight"), ws.x, M=M, N=D, K=D,
+                                              bias=eng.p32(p + "self_attn.out_proj.bias"), resid=ws.x)),
+                ("ln2", lambda: ops.layernorm(ws.x, eng.p32(p + "layer_norm2.weight"), eng.p32(p + "layer_norm2.bias"), ws.h2, rows=M, D=D, eps=eps)),
+                ("fc1", lambda: ops.gemm(ws.h2, eng.p16(p + "mlp.fc1.weight"), ws.m, M=M, N=F, K=D, bias=eng.p32(p + "mlp.fc1.bias"), act="quick_gelu")),
+                ("fc2", lambda: ops.gemm(ws.m, eng.p16(p + "mlp.fc2.weight"), ws.x, M=M, N=D, K=F, bias=eng.p32(p + "mlp.fc2.bias"), resid=ws.x)),
+            )
+            for name, fn in seq:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                evs.append((name, e0, e1))
+        torch.cuda.synchronize()
+        if rep > 0:
+            for name, e0, e1 in evs:
+                acc[name].append(e0.elapsed_time(e1))
+    return {n: sum(v) / len(v) for n, v in acc.items()}
 
 
 def run_ours(args):
@@ -674,56 +697,34 @@ def run_ours(args):
     eng = model.engine
     ws = eng.workspace(B)
     p = f"backbone.encoder.layers.{cfg.layers - 1}."
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    kt = time_layer_kernels(eng, ws, cfg, B)
+    layer_ms = sum(kt.values())
 
-    def gemm_roof(name, fn, flops, key, pre):
-        k_ms = time_kernel(fn, flush, pre)
+    def roof(name, key_t, flops, key_ncu):
+        k_ms = kt[key_t]
         ach = flops / (k_ms * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": ncu.get(key + "_dram_bytes") if use_ncu else None,
-                "tensor_pipe_active_pct_ncu": ncu.get(key + "_tensor_pipe_pct") if use_ncu else None,
-                "traffic_source": ncu.get("source"), "peak_source": pk_kind + " (burst: kernel timed alone, of measured)",
-                "launch_us": k_ms * 1e3, "flops_per_launch": flops,
-                "timing": "CUDA events per launch; before each: L2 flushed, then the producer of the input activations runs (step-like cache state)"}
-
-    g2w, g2b = eng.p32(p + "layer_norm2.weight"), eng.p32(p + "layer_norm2.bias")
-    w1, b1 = eng.p16(p + "mlp.fc1.weight"), eng.p32(p + "mlp.fc1.bias")
-    w2, b2 = eng.p16(p + "mlp.fc2.weight"), eng.p32(p + "mlp.fc2.bias")
-    wo, bo = eng.p16(p + "self_attn.out_proj.weight"), eng.p32(p + "self_attn.out_proj.bias")
-    lo, hi = eng.layout.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight")
-    wqkv = eng.flat16[lo:hi].view(3 * D, D)
-    lo, hi = eng.layout.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias")
-    bqkv = eng.flat32[lo:hi]
-
-    def k_ln2():
-        ops.layernorm(ws.x_mid, g2w, g2b, ws.h2, rows=M, D=D, eps=cfg.ln_eps)
-
-    def k_fc1():
-        ops.gemm(ws.h2, w1, ws.m, M=M, N=F, K=D, bias=b1, act="quick_gelu")
-
-    def k_fc2():
-        ops.gemm(ws.m, w2, ws.x_out, M=M, N=D, K=F, bias=b2, resid=ws.x_mid)
-
-    def k_qkv():
-        ops.gemm(ws.h1, wqkv, ws.qkv, M=M, N=3 * D, K=D, bias=bqkv)
-
-    def k_attn():
-        ops.flash_attn_fwd(ws.qkv, ws.ctx, B=B, S=cfg.tokens, H=cfg.heads, head_dim=cfg.head_dim, scale=cfg.head_dim ** -0.5)
-
-    def k_out():
-        ops.gemm(ws.ctx, wo, ws.x_mid, M=M, N=D, K=D, bias=bo, resid=ws.x)
+                "frac": ach / pk["bf16_tflops"], "traffic": ncu.get(key_ncu + "_dram_bytes") if use_ncu else None,
+                "tensor_pipe_active_pct_ncu": ncu.get(key_ncu + "_tensor_pipe_pct") if use_ncu else None,
+                "traffic_source": ncu.get("source"), "peak_source": pk_kind + " (burst figure, of measured)",
+                "launch_us": k_ms * 1e3, "flops_per_launch": flops, "share_of_layer": k_ms / layer_ms,
+                "timing": "CUDA events around every launch of a 12-layer sweep with each layer's own weights (step-like cache "
+                          "state; mean over %d launches)" % (4 * cfg.layers)}
 
     # fc2 is the launch with the largest share of the step (profiles/*_step_launches.txt)
-    roofline = gemm_roof("gemm_tc_kernel (MLP fc2 + bias + residual, fp32 out, M=%d N=%d K=%d)" % (M, D, F),
-                         k_fc2, 2.0 * M * D * F, "fc2_gemm", k_fc1)
-    roofline_fc1 = gemm_roof("gemm_tc_kernel (MLP fc1 + bias + quick_gelu, fp16 out, M=%d N=%d K=%d)" % (M, F, D),
-                             k_fc1, 2.0 * M * F * D, "fc1_gemm", k_ln2)
-    roofline_out = gemm_roof("gemm_tc_kernel (attention out-proj + bias + residual, fp32 out, M=%d N=%d K=%d)" % (M, D, D),
-                             k_out, 2.0 * M * D * D, "out_proj_gemm", k_attn)
-    roofline_attn = gemm_roof("flash_attn_fwd kernel (S=%d, H=%d, dh=%d)" % (cfg.tokens, cfg.heads, cfg.head_dim),
-                              k_attn, 4.0 * B * cfg.heads * cfg.tokens * cfg.tokens * cfg.head_dim, "flash_attn", k_qkv)
+    roofline = roof("gemm_tc_kernel (MLP fc2 + bias + residual, fp32 out, M=%d N=%d K=%d)" % (M, D, F), "fc2", 2.0 * M * D * F, "fc2_gemm")
+    roofline_fc1 = roof("gemm_tc_kernel (MLP fc1 + bias + quick_gelu, fp16 out, M=%d N=%d K=%d)" % (M, F, D), "fc1", 2.0 * M * F * D, "fc1_gemm")
+    roofline_qkv = roof("gemm_tc_kernel (fused q|k|v projection + bias, fp16 out, M=%d N=%d K=%d)" % (M, 3 * D, D), "qkv", 2.0 * M * 3 * D * D, "qkv_gemm")
+    roofline_out = roof("gemm_tc_kernel (attention out-proj + bias + residual, fp32 out, M=%d N=%d K=%d)" % (M, D, D), "out_proj", 2.0 * M * D * D, "out_proj_gemm")
+    roofline_attn = roof("flash_attn_fwd kernel (S=%d, H=%d, dh=%d)" % (cfg.tokens, cfg.heads, cfg.head_dim), "attn",
+                         4.0 * B * cfg.heads * cfg.tokens * cfg.tokens * cfg.head_dim, "flash_attn")
     roofline_attn["note"] = "head_dim 64: exp2 on the MUFU needs 2x the MMA cycles per score tile, see DESIGN.md"
-    del flush
+    ln_bytes = M * D * (4 + 2)
+    roofline_ln = {"bound": "hbm", "kernel": "layernorm_kernel (fp32 in, fp16 out, %d x %d)" % (M, D),
+                   "achieved": ln_bytes / (kt["ln1"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                   "frac": ln_bytes / (kt["ln1"] * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_us": kt["ln1"] * 1e3,
+                   "bytes_per_launch": ln_bytes, "share_of_layer": (kt["ln1"] + kt["ln2"]) / layer_ms,
+                   "note": "input just written by the previous GEMM: partly served from L2, so the fraction can exceed 1"}
     fl = flops_per_image(cfg)
     step_tflops = fl["fwd_bwd_ref_policy"] * B / (ms_per_step * 1e-3) / 1e12
     step_roof = {"flops_per_image": fl["fwd_bwd_ref_policy"], "achieved_tflops_per_gpu": step_tflops,
@@ -746,8 +747,9 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "h2d_gbs_measured": h2d_gbs, "h2d_ms_per_step_at_that_rate": h2d / h2d_gbs * 1e-6},
-        "roofline": roofline, "roofline_fc1": roofline_fc1, "roofline_out_proj": roofline_out,
-        "roofline_attention": roofline_attn, "roofline_step": step_roof, "final_losses": final_losses,
+        "roofline": roofline, "roofline_fc1": roofline_fc1, "roofline_qkv": roofline_qkv, "roofline_out_proj": roofline_out,
+        "roofline_attention": roofline_attn, "roofline_layernorm": roofline_ln, "roofline_step": step_roof,
+        "encoder_layer_us": {k: v * 1e3 for k, v in kt.items()}, "final_losses": final_losses,
         "host": {"cpu": cpu_model(), "cores": os.cpu_count()},
     }
 

@@ -116,8 +116,6 @@ int owl_rownorm_f16(const float* e, void* out_f16, int rows, int E, int query_mo
  * stores the sigmoid output (cx,cy,w,h) for the backward pass. */
 int owl_box_tail(const void* h_f16, const float* w, const float* bias, const float* box_bias, float* boxes,
                  float* sig, int M, int P, int D, void* stream);
-/* HF:398 softmax over the first n columns of each row of an fp16 [rows, ld] buffer, in place (n <= 1024). */
-int owl_softmax_rows_f16(void* scores_f16, long long rows, int n, int ld, void* stream);
 int owl_cast_f16(const float* src, void* dst_f16, long long n, float scale, void* stream);
 /* HF:379-404 fused attention forward: ctx[b, s, h*64 + d] = softmax(scale * q k^T) v for every (image, head), reading
  * the packed qkv buffer [B*S, 3*H*64] (q | k | v column blocks) and never materialising the scores (tcgen05: S and O
@@ -215,10 +213,6 @@ int owl_box_tail_bwd(const float* dboxes, const float* sig, const float* w2, con
                      int M, int D, void* stream);
 /* bias gradients: out[n] += (gscale ? gscale[1] : 1) * sum_m x[m, n]   (x fp16 or fp32, N and ld even). */
 int owl_colsum(const void* x, int is_f16, long long ld, int M, int N, const float* gscale, float* out, void* stream);
-/* HF:398 softmax backward: dS = P * (dP - sum(P dP)) * scale.  P fp16, dP fp32 (the subtraction cancels most of
- * its magnitude), dS fp16; all [rows, ld] with n <= 1024 valid columns. */
-int owl_softmax_bwd_f16(const void* probs_f16, const float* dprobs_f32, void* dscores_f16, long long rows, int n,
-                        int ld, float scale, void* stream);
 /* LayerNorm backward (HF:498,507; reference src/models.py:80): dx = dx_add + LN'(dy) (dx may be NULL when only the
  * parameter gradients are needed); dgamma / dbeta += 1/S * sums. */
 int owl_layernorm_bwd(const float* x, long long x_stride, const float* dy, long long dy_stride, const float* gamma,

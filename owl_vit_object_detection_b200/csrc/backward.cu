@@ -231,35 +231,6 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, int M, int 
   }
 }
 
-// ------------------------------------------------------------------ softmax backward (HF:398)
-// dS = P * (dP - sum_j P_j dP_j) * scale.   P fp16 [rows, ld], dP fp32 [rows, ld] (kept in fp32: the subtraction
-// cancels most of dP's magnitude), dS fp16 [rows, ld]; n <= 1024 valid columns.
-__global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __restrict__ dp, __half* __restrict__ ds,
-                                   long long rows, int n, int ld, float scale) {
-  pdl_grid_wait();
-  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const __half* pr = p + row * ld;
-  const float* dr = dp + row * ld;
-  __half* sr = ds + row * ld;
-  float pv[32], dv[32];
-  float dot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = lane + 32 * i;
-    pv[i] = c < n ? __half2float(pr[c]) : 0.f;
-    dv[i] = c < n ? dr[c] : 0.f;
-    dot += pv[i] * dv[i];
-  }
-  dot = bw_warp_sum(dot);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = lane + 32 * i;
-    if (c < n) sr[c] = __float2half_rn(pv[i] * (dv[i] - dot) * scale);
-  }
-}
-
 // ------------------------------------------------------------------ LayerNorm backward
 // y = xh * gamma + beta, xh = (x - mean) * rstd.
 //   dx = rstd * (g - mean(g) - xh * mean(g * xh)),  g = dy * gamma          (+ dx_add when given)
@@ -576,16 +547,6 @@ extern "C" int owl_colsum(const void* x, int is_f16, long long ld, int M, int N,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (is_f16) OWL_LAUNCH(colsum_kernel<__half>, grid, block, 0, s, static_cast<const __half*>(x), ld, M, N, gscale, out);
   else OWL_LAUNCH(colsum_kernel<float>, grid, block, 0, s, static_cast<const float*>(x), ld, M, N, gscale, out);
-  OWL_CUDA(cudaGetLastError());
-  return OWL_OK;
-}
-
-extern "C" int owl_softmax_bwd_f16(const void* probs, const float* dprobs, void* dscores, long long rows, int n,
-                                   int ld, float scale, void* stream) {
-  OWL_CHECK_ARG(probs && dprobs && dscores && rows > 0 && n > 0 && n <= 1024 && ld >= n,
-                "softmax_bwd: bad arguments (n <= 1024)");
-  OWL_LAUNCH(softmax_bwd_kernel, static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __half*>(probs), dprobs, static_cast<__half*>(dscores), rows, n, ld, scale);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

@@ -310,37 +310,6 @@ __global__ void box_tail_kernel(const __half* __restrict__ h, const float* __res
   }
 }
 
-// ------------------------------------------------------------------ softmax over rows of fp16 scores (in place)
-// HF:398 softmax in fp32; rows of length n inside a [rows, ld] buffer; columns >= n are left untouched.
-__global__ void softmax_rows_kernel(__half* __restrict__ s, long long rows, int n, int ld) {
-  pdl_grid_wait();
-  const long long row = blockIdx.x * 1LL * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  __half* r = s + row * ld;
-  float v[32];
-  float m = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = c < n ? __half2float(r[c]) : -INFINITY;
-    m = fmaxf(m, v[i]);
-  }
-  m = warp_max(m);
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] = (lane + 32 * i) < n ? __expf(v[i] - m) : 0.f;
-    sum += v[i];
-  }
-  const float inv = 1.0f / warp_sum(sum);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = lane + 32 * i;
-    if (c < n) r[c] = __float2half_rn(v[i] * inv);
-  }
-}
-
 // ------------------------------------------------------------------ fp32 -> fp16 cast with scale
 __global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n, float scale) {
   pdl_grid_wait();
@@ -443,14 +412,6 @@ extern "C" int owl_box_tail(const void* h, const float* w, const float* bias, co
   OWL_CHECK_ARG(D % 8 == 0, "box_tail: D %% 8 != 0");
   OWL_LAUNCH(box_tail_kernel, row_blocks(M), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(h), w, bias, box_bias, boxes, sig, M, P, D);
-  OWL_CUDA(cudaGetLastError());
-  return OWL_OK;
-}
-
-extern "C" int owl_softmax_rows_f16(void* scores, long long rows, int n, int ld, void* stream) {
-  OWL_CHECK_ARG(scores && rows > 0 && n > 0 && n <= 1024 && ld >= n, "softmax_rows: bad arguments (n <= 1024)");
-  OWL_LAUNCH(softmax_rows_kernel, row_blocks(rows), ROW_WARPS * 32, 0, static_cast<cudaStream_t>(stream), 
-      static_cast<__half*>(scores), rows, n, ld);
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

@@ -139,11 +139,6 @@ def box_tail(h16, w, bias, box_bias, boxes, sig, *, M: int, P: int, D: int):
     return boxes
 
 
-def softmax_rows_f16(scores: torch.Tensor, *, rows: int, n: int, ld: int):
-    check(lib().owl_softmax_rows_f16(_vp(scores), ctypes.c_longlong(rows), n, ld, _sp()), "owl_softmax_rows_f16")
-    return scores
-
-
 _L2_WINDOW = (0, 0)
 
 
@@ -328,13 +323,6 @@ def colsum(x: torch.Tensor, out: torch.Tensor, *, M: int, N: int, gscale=None, l
     check(lib().owl_colsum(_vp(x), int(x.dtype == torch.float16), _ll(x.stride(-2) if ld is None else ld), M, N,
                            _vp(gscale), _vp(out), _sp()), "owl_colsum")
     return out
-
-
-def softmax_bwd_f16(probs, dprobs32, dscores16, *, rows: int, n: int, ld: int, scale: float):
-    assert dprobs32.dtype == torch.float32 and dscores16.dtype == torch.float16
-    check(lib().owl_softmax_bwd_f16(_vp(probs), _vp(dprobs32), _vp(dscores16), _ll(rows), n, ld, _fl(scale), _sp()),
-          "owl_softmax_bwd_f16")
-    return dscores16
 
 
 def layernorm_bwd(x, dy, gamma, dgamma, dbeta, *, rows: int, D: int, eps: float, gscale=None, dx=None, dx_add=None,
