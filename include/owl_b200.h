@@ -164,10 +164,12 @@ int owl_postprocess(const float* boxes, const float* sims, int B, int P, int C, 
  * and 2 for an infeasible assignment; the caller zeroes it and checks it when it syncs anyway.
  */
 /* src/matcher.py:103-131.  costT [B,Tmax,P] f32 (target-major so that the solver's scans are coalesced):
- * costT[b][t][p] = (L1(box_p, tbox_t) - softmax(sims[b,p])[label_t]) - GIoU(box_p, tbox_t). */
+ * costT[b][t][p] = (cost_bbox * L1(box_p, tbox_t) + cost_class * -softmax(sims[b,p])[label_t]) + cost_giou * -GIoU(box_p,
+ * tbox_t), the weights of HungarianMatcher.__init__ (src/matcher.py:55-60; the reference uses 1, 1, 1).  status bits:
+ * 1 degenerate box, 2 infeasible, 4 num_targets outside [0, Tmax], 8 label outside [0, C). */
 int owl_matcher_cost(const float* sims, const float* boxes, const long long* labels, const float* tboxes,
                      const int* num_targets, float* costT, int B, int P, int C, int Tmax, int* status,
-                     void* stream);
+                     float cost_class, float cost_bbox, float cost_giou, void* stream);
 /* src/matcher.py:135-137 (scipy.optimize.linear_sum_assignment).  match_pred [B,Tmax] i32: prediction assigned
  * to each target, -1 for padding.  Index-exact with SciPy including its tie rule whenever num_targets < P
  * (SciPy transposes the problem only when rows > cols; the reference always has P = 576 > T). */

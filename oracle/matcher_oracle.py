@@ -91,17 +91,19 @@ def generalized_box_iou(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
 
 
 def cost_matrix(sims: torch.Tensor, boxes: torch.Tensor, labels: torch.Tensor,
-                tboxes: torch.Tensor) -> torch.Tensor:
+                tboxes: torch.Tensor, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1) -> torch.Tensor:
     """One image: sims [P,C] f32, boxes [P,4] xyxy, labels [T] i64, tboxes [T,4] -> C [P,T] f32.
     reference src/matcher.py:106-131 with the three weights = 1 (:58-60).  The L1 term is the
     sequential sum ((|dx0|+|dy0|)+|dx1|)+|dy1|, bit-identical to torch.cdist(p=1) on CPU.
     Sum order: (L1 + (-p)) + (-giou)  (:127-131)."""
     prob = sims.float().softmax(-1)
-    cost_class = -prob[:, labels]
     d = (boxes[:, None, :] - tboxes[None, :, :]).abs()
-    cost_bbox = ((d[..., 0] + d[..., 1]) + d[..., 2]) + d[..., 3]
-    cost_giou = -generalized_box_iou(boxes, tboxes)
-    return (cost_bbox + cost_class) + cost_giou
+    cost_bbox_m = ((d[..., 0] + d[..., 1]) + d[..., 2]) + d[..., 3]
+    cost_giou_m = -generalized_box_iou(boxes, tboxes)
+    w_class, w_bbox, w_giou = cost_class, cost_bbox, cost_giou
+    cost_class = -prob[:, labels]
+    # reference src/matcher.py:127-131: self.cost_bbox * cost_bbox + self.cost_class * cost_class + self.cost_giou * cost_giou
+    return (w_bbox * cost_bbox_m + w_class * cost_class) + w_giou * cost_giou_m
 
 
 def hungarian(sims: torch.Tensor, boxes: torch.Tensor, labels: Sequence[torch.Tensor],

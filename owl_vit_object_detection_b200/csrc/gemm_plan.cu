@@ -1,4 +1,5 @@
 #include "gemm_plan.h"
+#include <stdlib.h>
 
 namespace owl {
 
@@ -71,6 +72,8 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
   gs.M = a.M; gs.N = a.N; gs.K = a.K;
   gs.G = G; gs.H = a.heads;
   gs.split_k = a.split_k;
+  static const int debug = [] { const char* e = getenv("OWL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  gs.debug = debug;
 
   auto build_operand = [&](const void* base, bool mn, int rows_mn, long long ld, long long outer_stride,
                            long long head_stride, int head_col, int box_rows_k_major, CUtensorMap* tm,
@@ -122,6 +125,20 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
     e.vec_ok = al16(a.out, a.ldo) && al16(a.pre_out, a.ld_pre) && al16(a.act_src, a.ld_act_src) &&
                (a.o_outer_stride * 2) % 16 == 0 && (a.o_head_stride * 2) % 16 == 0 &&
                (a.act_src_outer_stride * 2) % 16 == 0 && (a.act_src_head_stride * 2) % 16 == 0;
+    // bulk-tensor stores of the output tiles (one [M, N] matrix, 16-byte aligned rows; every N tile >= 128 drains
+    // 64-column slices per epilogue warp)
+    static const bool tma_off = [] { const char* v = getenv("OWL_GEMM_TMA_STORE"); return v && v[0] == '0'; }();
+    e.use_tma = (!tma_off && G == 1 && e.vec_ok && p.bn >= 128) ? 1 : 0;
+    if (e.use_tma) {
+      rc = make_tensor_map_f16(&e.tm_out, a.out, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M), 1,
+                               static_cast<uint64_t>(a.ldo), 0, 64, 32);
+      if (rc) return rc;
+      if (a.pre_out) {
+        rc = make_tensor_map_f16(&e.tm_pre, a.pre_out, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M), 1,
+                                 static_cast<uint64_t>(a.ld_pre), 0, 64, 32);
+        if (rc) return rc;
+      }
+    }
   } else if (a.epilogue == 1) {
     EpiF32::Params& e = p.p32;
     e.out = static_cast<float*>(a.out);

@@ -34,10 +34,10 @@ template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1, int MINB = 1>
 int gemm_launch_one(const GemmPlan& p, const typename Epi::Params& ep, cudaStream_t s) {
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CM, MINB>;
   static SmemOptIn optin;  // per instantiation
-  OWL_CUDA(ensure_smem(optin, kern, gemm_smem_bytes(BN / CM, MINB)));
+  OWL_CUDA(ensure_smem(optin, kern, gemm_smem_bytes(BN, CM, MINB)));
   // persistent grid: one CTA per SM slot the flavour is built for
   const int grid = MINB == 1 ? p.grid : static_cast<int>(std::min<long long>(p.tiles, 1LL * MINB * num_sms()));
-  OWL_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(BN / CM, MINB), s, CM, p.tmA, p.tmB, p.gs, ep));
+  OWL_CUDA(launch_pdl(kern, dim3(grid), dim3(gemm_threads(BN)), gemm_smem_bytes(BN, CM, MINB), s, CM, p.tmA, p.tmB, p.gs, ep));
   OWL_CUDA(cudaGetLastError());
   return OWL_OK;
 }

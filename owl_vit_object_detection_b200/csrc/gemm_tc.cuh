@@ -16,8 +16,8 @@
 // * a "batch" dimension g = (outer, head) addresses per-head attention matrices inside the packed
 //   [tokens, 3*hidden] QKV buffer through the tensor map's third coordinate / a column offset.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4, column half = (warp_idx - 2) / 4).
+// Warp roles: warps 0 .. E-1 = epilogue (E = gemm_epi_warps(BN); TMEM lane quadrant = warp_idx % 4, column part =
+// warp_idx / 4, <= 64 columns each), warp E = TMA producer, warp E+1 = MMA issuer + TMEM owner.
 #pragma once
 #include "ptx.cuh"
 
@@ -25,9 +25,15 @@ namespace owl {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 fp16 = one 128-byte swizzle row
-constexpr int GEMM_EPI_WARPS = 8;   // two per TMEM lane quadrant, each draining half of the tile's columns
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
-constexpr int GEMM_SMEM_BUDGET = 192 * 1024;
+constexpr int GEMM_SMEM_LIMIT = 227 * 1024;   // opt-in shared memory per CTA on sm_100a
+
+// Epilogue warps of a tile: every warp drains <= 64 accumulator columns of one TMEM lane quadrant, so a 256-wide tile
+// has sixteen of them (four per scheduler), a 192-wide one twelve.  With eight warps per tile (two per scheduler) the
+// epilogue of the K = 768 layer GEMMs - a serial chain of tcgen05.ld / MUFU / shared-memory transposition / global
+// store latencies - took ~11k clk per 128 x 256 tile against ~6k clk of MMAs, i.e. the tensor pipe idled 45 % of the
+// time waiting for a free accumulator (ncu: sm__pipe_tensor_cycles_active 55 %).
+__host__ __device__ constexpr int gemm_epi_warps(int BN) { return BN >= 128 ? 4 * (BN / 64) : 8; }
+__host__ __device__ constexpr int gemm_threads(int BN) { return 64 + 32 * gemm_epi_warps(BN); }
 
 struct GemmShape {
   int M, N, K;       // per-batch logical sizes
@@ -36,21 +42,26 @@ struct GemmShape {
   int a_sb, a_sh;    // A's 3rd tensor-map coordinate = outer * a_sb + head * a_sh
   int b_col_off, b_sb, b_sh;
   int split_k;       // K is cut into split_k slices (epilogue must then reduce atomically)
+  int debug;         // dev only (OWL_GEMM_DEBUG): 1 = epilogue does nothing, 2 = no TMA loads (MMAs run on stale smem),
+                     // 4 = no loads and no MMAs (epilogue only)
 };
 
-__host__ __device__ constexpr int gemm_stage_bytes(int BN) { return (GEMM_BM + BN) * GEMM_BK * 2; }
+constexpr int GEMM_EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B transposition buffer
+constexpr int GEMM_EPI_BIAS_BYTES = 256;    // per epilogue warp: the bias of its <= 64 columns (broadcast reads)
+// BN = N tile of the (cluster) tile, CM = CTAs of the cluster along M (each stages BN / CM rows of B)
+__host__ __device__ constexpr int gemm_stage_bytes(int BN, int CM = 1) { return (GEMM_BM + BN / CM) * GEMM_BK * 2; }
 // MINB = CTAs per SM the kernel is built for.  2 is the flavour for short-K, epilogue-dominated problems (the
 // attention-backward GEMMs, K = 64: one k-block per tile): a 64 KB operand ring and <= 102 registers let two CTAs
-// share an SM, i.e. sixteen epilogue warps instead of eight hide each other's latencies.
-__host__ __device__ constexpr int gemm_num_stages(int BN, int MINB = 1) {
-  const int budget = MINB == 2 ? 64 * 1024 : GEMM_SMEM_BUDGET;
-  return budget / gemm_stage_bytes(BN) > 8 ? 8 : budget / gemm_stage_bytes(BN);
+// share an SM.
+__host__ __device__ constexpr int gemm_num_stages(int BN, int CM = 1, int MINB = 1) {
+  const int budget = MINB == 2 ? 64 * 1024
+                               : GEMM_SMEM_LIMIT - gemm_epi_warps(BN) * (GEMM_EPI_STAGE_BYTES + GEMM_EPI_BIAS_BYTES) - 1024 - 256;
+  const int n = budget / gemm_stage_bytes(BN, CM);
+  return n > 8 ? 8 : n;
 }
-constexpr int GEMM_EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B transposition buffer
-// BN here is the number of B rows ONE CTA stages (BN / 2 in the pair flavour)
-__host__ __device__ constexpr int gemm_smem_bytes(int BN, int MINB = 1) {
-  return gemm_num_stages(BN, MINB) * gemm_stage_bytes(BN) + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 /*align slack*/ +
-         256 /*barriers*/;
+__host__ __device__ constexpr int gemm_smem_bytes(int BN, int CM = 1, int MINB = 1) {
+  return gemm_num_stages(BN, CM, MINB) * gemm_stage_bytes(BN, CM) +
+         gemm_epi_warps(BN) * (GEMM_EPI_STAGE_BYTES + GEMM_EPI_BIAS_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 __host__ __device__ constexpr int gemm_tmem_cols(int BN) {
   return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -78,11 +89,11 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t base, int k16) {
 //   full_bar   leader only: its own arrive.expect_tx(2 x stage bytes) + complete_tx from both CTAs' TMA loads
 //   empty_bar  per CTA, count 1: the leader's tcgen05.commit is multicast to both CTAs
 //   tfull_bar  per CTA, count 1: same multicast commit after the last k-block of a tile
-//   tempty_bar leader only, count 2 x epilogue warps: the peer's epilogue warps arrive remotely
+//   tempty_bar leader only, count CM x epilogue warps: the peer's epilogue warps arrive remotely
 template <int BN, bool A_MN, bool B_MN, class Epi, int CM = 1, int MINB = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, MINB)
+__global__ void __launch_bounds__(gemm_threads(BN), MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmShape gs, const typename Epi::Params ep) {
+               const GemmShape gs, const __grid_constant__ typename Epi::Params ep) {
   static_assert(CM == 1 || CM == 2, "1 = single CTA, 2 = CTA pair (cta_group::2)");
   static_assert(CM == 1 || !A_MN, "the pair flavour is built for K-major A");
   static_assert(!B_MN || (BN / 64) % CM == 0, "MN-major B: whole 64-wide chunks per CTA");
@@ -90,7 +101,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int BN_CTA = BN / CM;                       // B rows held by one CTA
   constexpr int B_BYTES = BN_CTA * GEMM_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = gemm_num_stages(BN_CTA, MINB);
+  constexpr int STAGES = gemm_num_stages(BN, CM, MINB);
+  constexpr int EPI_WARPS = gemm_epi_warps(BN);
+  constexpr int PARTS = EPI_WARPS / 4;                  // column parts of a tile, one epilogue warp per (quadrant, part)
+  static_assert(STAGES >= 2, "operand ring too small");
   static_assert(MINB == 1 || (CM == 1 && 2 * gemm_tmem_cols(BN) <= 512), "two CTAs per SM: both accumulators must fit TMEM");
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN);
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
@@ -99,7 +113,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;   // 4 KB per epilogue warp
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES);
+  uint8_t* epi_bias = epi_stage + EPI_WARPS * GEMM_EPI_STAGE_BYTES;   // 256 B per epilogue warp
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_bias + EPI_WARPS * GEMM_EPI_BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
@@ -107,6 +122,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Warp roles: the epilogue warps come first (warp w drains TMEM lane quadrant w % 4, column part w / 4), the two
+  // single-thread control warps LAST: the sub-partition arbiter prefers the highest warp id among eligible warps, and
+  // the MMA issuer's handful of instructions per k-block must never queue behind four busy epilogue warps.
+  constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
 
   const int mb = (gs.M + GEMM_BM - 1) / GEMM_BM;
   const int nb = (gs.N + BN - 1) / BN;
@@ -128,12 +147,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * CM);
+      mbar_init(&tempty_bar[s], EPI_WARPS * CM);
     }
     fence_barrier_init();
   }
   if constexpr (CM > 1) cluster_sync_all();   // both CTAs are resident with initialised barriers before pair ops
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     if constexpr (CM == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     else { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
   }
@@ -144,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   pdl_grid_wait();   // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     // ------------------------------------------------ TMA producer (every CTA fills its own shared memory)
     if (lane == 0) {
       int stage = 0;
@@ -161,12 +180,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m0 = m_blk * GEMM_BM;
         const int n0 = n_blk * BN + crank * BN_CTA;          // this CTA's slice of the B tile
         const int kb0 = ks * kb_per;
-        const int kb1 = min(kb0 + kb_per, kb_total);
+        const int kb1 = (gs.debug & 4) ? kb0 : min(kb0 + kb_per, kb_total);   // dev: 4 = epilogue only
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          if constexpr (CM == 1) {
+          if (gs.debug & 2) {   // dev: hand the slot over without loading anything
+            if (CM == 1 || leader) mbar_arrive(&full_bar[stage]);
+          } else if constexpr (CM == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             if constexpr (!A_MN) {
               tma_load_3d(sa, &tmA, &full_bar[stage], kb * GEMM_BK + a_c, m0, a_b);
@@ -198,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ------------------------------------------------ MMA issuer (pair flavour: leader CTA only)
     if (CM == 1 || leader) {
       constexpr uint32_t IDESC = make_idesc_f16(GEMM_BM * CM, BN, A_MN, B_MN);
@@ -217,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = t % tiles_per_g;
         const int ks = r / (mbc * nb);
         const int kb0 = ks * kb_per;
-        const int kb1 = min(kb0 + kb_per, kb_total);
+        const int kb1 = (gs.debug & 4) ? kb0 : min(kb0 + kb_per, kb_total);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -252,9 +273,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------ epilogue warps
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;     // which half of the tile's columns it drains
-    constexpr int NH = BN / 2;
-    const uint32_t stage_buf = smem_u32(epi_stage + (warp - 2) * GEMM_EPI_STAGE_BYTES);
+    const int half = warp >> 2;           // which part of the tile's columns it drains
+    constexpr int NH = BN / PARTS;
+    const uint32_t stage_buf = smem_u32(epi_stage + warp * GEMM_EPI_STAGE_BYTES);
+    const uint32_t bias_buf = smem_u32(epi_bias + warp * GEMM_EPI_BIAS_BYTES);
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int g = t / tiles_per_g;
@@ -276,10 +298,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb0 = ks * kb_per;
       // a split whose K range is empty contributes nothing (can happen when split_k does not divide)
       const bool has_k = kb0 < kb_total;
-      if constexpr (Epi::kSplitColumns) {
-        Epi::template run<NH>(ep, pre, taddr + half * NH, stage_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
+      if (gs.debug & 1) {
+        // dev: accumulator handed back untouched
+      } else if constexpr (Epi::kSplitColumns) {
+        Epi::template run<NH>(ep, pre, taddr + half * NH, stage_buf, bias_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
       } else if (half == 0) {
-        Epi::template run<BN>(ep, pre, taddr, stage_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
+        Epi::template run<BN>(ep, pre, taddr, stage_buf, bias_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
       }
       tc_fence_before();
       __syncwarp();
@@ -288,13 +312,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread owns the accumulator hand-off
       }
     }
+    tma_store_wait_all();   // bulk-tensor stores issued by this thread (Epi with a TMA store path) are complete
   }
 
   tc_fence_before();
   __syncthreads();
   // no CTA may exit (or free TMEM) while its partner can still touch its shared memory, barriers or TMEM
   if constexpr (CM > 1) cluster_sync_all();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     if constexpr (CM == 1) tmem_dealloc(tmem_base, TMEM_COLS);
     else tmem_dealloc_2sm(tmem_base, TMEM_COLS);
@@ -455,6 +480,9 @@ struct EpiF16Params {
   int vec_ok;            // all of out / pre_out / dact_src rows are 16-byte aligned
   float alpha;
   const float* alpha_dev;  // optional device scalar multiplied into alpha
+  int use_tma;             // out (and pre_out) are written with bulk-tensor stores through tm_out / tm_pre
+  CUtensorMap tm_out;      // [M, N] fp16, box 64 columns x 32 rows, 128-byte swizzle (= the staging tile's layout)
+  CUtensorMap tm_pre;
 };
 
 template <int ACT>
@@ -469,8 +497,9 @@ struct EpiF16 {
     pre.bias = load_bias_slice<BN>(p.bias, n0, N, lane);
   }
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, const Pre& pre, uint32_t taddr, uint32_t stage, int g,
-                                             int row0, int lane, int n0, int M, int Nfull, bool has_k) {
+  static __device__ __forceinline__ void run(const Params& p, const Pre& pre, uint32_t taddr, uint32_t stage,
+                                             uint32_t bias_smem, int g, int row0, int lane, int n0, int M, int Nfull,
+                                             bool has_k) {
     const int N = min(Nfull, n0 + BN);  // this warp's column slice ends here
     const int outer = g / p.H, head = g - outer * p.H;
     __half* out = p.out + outer * p.o_sb + head * p.o_sh;
@@ -479,6 +508,19 @@ struct EpiF16 {
     constexpr bool kGrad = (ACT == ACT_QGELU_GRAD || ACT == ACT_GELU_GRAD || ACT == ACT_SMAX_GRAD);
     constexpr bool kRowVec = (ACT == ACT_EXP_ROW || ACT == ACT_SMAX_GRAD);
     if (row0 >= M) return;  // warp-uniform: nothing of this warp's 32 rows is inside the matrix
+    // Fast path of the layer GEMMs: the warp's slice is whole 64-column chunks, the staging tile (32 rows x 128 B,
+    // 16-byte chunks XOR-swizzled with the row) is exactly a 128B-swizzled TMA box, so one elected lane stores it with
+    // a bulk-tensor copy (rows / columns outside the matrix are clipped by the TMA unit) instead of eight LDS + STG
+    // with per-row address arithmetic and bounds checks per lane; the bias of the slice sits in shared memory
+    // (written once per tile from the prologue's coalesced load) and is read back as broadcasts.
+    const bool tma = (BN % 64 == 0) && p.use_tma != 0;
+    const bool smem_bias = (BN % 64 == 0) && p.bias != nullptr;
+    if (smem_bias) {
+      if (lane < BN / 4)
+        sts128(bias_smem + lane * 16, make_uint4(__float_as_uint(pre.bias.x), __float_as_uint(pre.bias.y),
+                                                 __float_as_uint(pre.bias.z), __float_as_uint(pre.bias.w)));
+      __syncwarp();
+    }
     const __half* dsrc = kGrad ? p.dact_src + outer * p.d_sb + head * p.d_sh : nullptr;
     float rv = 0.f;         // row phase: thread t owns row t of the warp's 32
     if constexpr (kRowVec) rv = __ldg(p.rowvec + g * p.rowvec_stride + min(row0 + lane, M - 1));
@@ -510,7 +552,15 @@ struct EpiF16 {
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
           }
           if (p.bias) {
-            if (n + h * 32 + 32 <= N) {
+            if (smem_bias) {
+              // all lanes read the same eight 16-byte words of the slice's bias from shared memory (broadcasts)
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const uint4 bq = lds128(bias_smem + (c * 16 + h * 8 + q) * 16);
+                v[4 * q] += __uint_as_float(bq.x); v[4 * q + 1] += __uint_as_float(bq.y);
+                v[4 * q + 2] += __uint_as_float(bq.z); v[4 * q + 3] += __uint_as_float(bq.w);
+              }
+            } else if (n + h * 32 + 32 <= N) {
               // all lanes read the same eight 16-byte words: one broadcast transaction each (no shuffles)
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + n + h * 32);
 #pragma unroll
@@ -553,10 +603,22 @@ struct EpiF16 {
             sts128(sa, pk);
           }
         }
-        __syncwarp();
-        if (pass == 0) tile_store_f16(p.pre_out, p.ld_pre, row0, n, M, N, stage, lane, vec_ok);
-        else tile_store_f16(out, p.ldo, row0, n, M, N, stage, lane, vec_ok);
-        __syncwarp();
+        if (tma) {
+          // generic-proxy writes of the staging tile -> visible to the async proxy, then one lane stores the box
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(pass == 0 ? &p.tm_pre : &p.tm_out, stage, n, row0, 0);
+            tma_store_commit();
+            tma_store_wait_read();     // the tile may be overwritten by the next pass / chunk / output tile
+          }
+          __syncwarp();
+        } else {
+          __syncwarp();
+          if (pass == 0) tile_store_f16(p.pre_out, p.ld_pre, row0, n, M, N, stage, lane, vec_ok);
+          else tile_store_f16(out, p.ldo, row0, n, M, N, stage, lane, vec_ok);
+          __syncwarp();
+        }
       }
     }
   }
@@ -709,8 +771,10 @@ struct EpiF32 {
     }
   }
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, Pre& pre, uint32_t taddr, uint32_t stage, int g,
-                                             int row0, int lane, int n0, int M, int N, bool has_k) {
+  static __device__ __forceinline__ void run(const Params& p, Pre& pre, uint32_t taddr, uint32_t stage,
+                                             uint32_t bias_smem, int g, int row0, int lane, int n0, int M, int N,
+                                             bool has_k) {
+    (void)bias_smem;
     const int outer = g / p.H, head = g - outer * p.H;
     float* out = p.out + outer * p.o_sb + head * p.o_sh;
     const bool vec_ok = p.vec_ok != 0;
@@ -724,9 +788,11 @@ struct EpiF32 {
       const long long step = 4LL * p.ldo;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        // next chunk's line-phase operands: in flight behind this chunk's work
-        float4 nadd[8], nb4;
-        if (c + 1 < BN / 32) lean_fetch(p, out, row0, n0 + (c + 1) * 32, M, lane, nadd, nb4);
+        // line-phase operands of this chunk: chunk 0's were fetched in the prologue (before the accumulator wait);
+        // later chunks fetch theirs here, in flight behind the TMEM load and the row phase.  (With four epilogue
+        // warps per scheduler the other warps cover this latency; a second register set for the next chunk's addend
+        // would push the 576-thread flavours over their register budget.)
+        if (c > 0) lean_fetch(p, out, row0, n0 + c * 32, M, lane, pre.add, pre.b4);
         // row phase: accumulator -> staging (thread t owns row t)
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
@@ -754,11 +820,6 @@ struct EpiF32 {
           }
         }
         __syncwarp();
-        if (c + 1 < BN / 32) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pre.add[i] = nadd[i];
-          pre.b4 = nb4;
-        }
       }
       return;
     }
@@ -840,9 +901,10 @@ struct EpiPool3 {
   template <int BN>
   static __device__ __forceinline__ void prologue(const Params&, Pre&, int, int, int, int, int, int) {}
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, const Pre&, uint32_t taddr, uint32_t stage, int g,
-                                             int row0, int lane, int n0, int M, int N, bool has_k) {
-    (void)g; (void)has_k; (void)stage;
+  static __device__ __forceinline__ void run(const Params& p, const Pre&, uint32_t taddr, uint32_t stage,
+                                             uint32_t bias_smem, int g, int row0, int lane, int n0, int M, int N,
+                                             bool has_k) {
+    (void)g; (void)has_k; (void)stage; (void)bias_smem;
     const int m = row0 + lane;
 #pragma unroll 1
     for (int c = 0; c * 96 < BN; ++c) {

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(COST_THREADS)
 matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ boxes,
                     const long long* __restrict__ labels, const float* __restrict__ tboxes,
                     const int* __restrict__ num_targets, float* __restrict__ costT, int P, int C, int Tmax,
-                    int* __restrict__ status) {
+                    int* __restrict__ status, float w_class, float w_bbox, float w_giou) {
   pdl_grid_wait();
   extern __shared__ float sm[];
   float* prob = sm;                                   // [64][C + 1]
@@ -179,8 +179,10 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
                                  fabsf(fsub(pb.x1, tb.x1))), fabsf(fsub(pb.y1, tb.y1)));
       const float pr = prob[row * (C + 1) + tlab[t]];
       const float gi = giou_pair(pb, tb);
-      // (cost_bbox + cost_class) + cost_giou with cost_class = -p, cost_giou = -giou (src/matcher.py:127-131)
-      costT[(1LL * b * Tmax + t) * P + p] = fsub(fsub(l1, pr), gi);
+      // (w_bbox * cost_bbox + w_class * cost_class) + w_giou * cost_giou with cost_class = -p, cost_giou = -giou
+      // (src/matcher.py:127-131; every product and sum rounds separately, like the torch ops).  With the reference's
+      // weights (all 1, src/matcher.py:58-60) the products are exact and this is (l1 - p) - giou bit for bit.
+      costT[(1LL * b * Tmax + t) * P + p] = fadd(fadd(fmul(w_bbox, l1), fmul(w_class, -pr)), fmul(w_giou, -gi));
     }
   }
 }
@@ -729,7 +731,7 @@ using namespace owl;
 
 extern "C" int owl_matcher_cost(const float* sims, const float* boxes, const long long* labels, const float* tboxes,
                                 const int* num_targets, float* costT, int B, int P, int C, int Tmax, int* status,
-                                void* stream) {
+                                float cost_class, float cost_bbox, float cost_giou, void* stream) {
   OWL_CHECK_ARG(sims && boxes && labels && tboxes && num_targets && costT && status, "matcher_cost: null argument");
   OWL_CHECK_ARG(B > 0 && P > 0 && C > 0 && Tmax > 0, "matcher_cost: empty dimension");
   OWL_CHECK_ARG(C <= 256, "matcher_cost: C = %d classes is more than the 256 this kernel keeps in registers", C);
@@ -745,12 +747,12 @@ extern "C" int owl_matcher_cost(const float* sims, const float* boxes, const lon
       static SmemOptIn optin;                                                                                       \
       OWL_CUDA(ensure_smem(optin, matcher_cost_kernel<NV, true>, 100 * 1024));                                      \
       OWL_LAUNCH((matcher_cost_kernel<NV, true>), grid, COST_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, \
-                 costT, P, C, Tmax, status);                                                                        \
+                 costT, P, C, Tmax, status, cost_class, cost_bbox, cost_giou);                                                                        \
     } else {                                                                                                        \
       static SmemOptIn optin;                                                                                       \
       OWL_CUDA(ensure_smem(optin, matcher_cost_kernel<NV, false>, 100 * 1024));                                     \
       OWL_LAUNCH((matcher_cost_kernel<NV, false>), grid, COST_THREADS, smem, s, sims, boxes, labels, tboxes, num_targets, \
-                 costT, P, C, Tmax, status);                                                                        \
+                 costT, P, C, Tmax, status, cost_class, cost_bbox, cost_giou);                                                                        \
     }                                                                                                               \
     break;
   switch (nvec) {

@@ -81,6 +81,19 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tiled store shared -> global (bulk async group of the issuing thread).  The shared-memory tile must be in the
+// tensor map's swizzle layout; elements outside the tensor are clipped by the TMA unit.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING shared memory (the staging tile may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups of this thread are complete (writes performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Same, written to the same shared-memory offset of every CTA in `cta_mask` of this cluster; each destination
 // CTA's mbarrier (same offset) receives the complete_tx.
 __device__ __forceinline__ void tma_load_3d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,

@@ -79,9 +79,8 @@ class HungarianMatcher(nn.Module):
 
     def __init__(self, n_classes: int, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1):
         super().__init__()
-        if not (cost_class == 1 and cost_bbox == 1 and cost_giou == 1):
-            # the reference never uses other weights (src/matcher.py:58-60); the kernel fixes them at 1
-            raise NotImplementedError("cost weights other than 1 are not built")
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"    # src/matcher.py:62-64
+        self.cost_class, self.cost_bbox, self.cost_giou = float(cost_class), float(cost_bbox), float(cost_giou)
         self.n_classes = n_classes
         self._buf: Dict[tuple, _Buffers] = {}
 
@@ -99,7 +98,8 @@ class HungarianMatcher(nn.Module):
         buf.generation += 1
         buf.status.zero_()
         with torch.cuda.device(sims.device):
-            ops.matcher_cost(sims, boxes, lab, box, nt, buf.costT, buf.status)
+            ops.matcher_cost(sims, boxes, lab, box, nt, buf.costT, buf.status, self.cost_class, self.cost_bbox,
+                             self.cost_giou)
             ops.lsap(buf.costT, nt, buf.match, buf.status)
         return buf
 

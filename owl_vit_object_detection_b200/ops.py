@@ -204,14 +204,16 @@ def cast_f16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
 
 
 # ------------------------------------------------------------------------------------------ matcher + loss
-def matcher_cost(sims, boxes, labels, tboxes, num_targets, costT, status):
+def matcher_cost(sims, boxes, labels, tboxes, num_targets, costT, status, cost_class: float = 1.0,
+                 cost_bbox: float = 1.0, cost_giou: float = 1.0):
     """reference src/matcher.py:103-131 -> costT [B,Tmax,P] (owl_matcher_cost)."""
     B, P, C = sims.shape
     Tmax = labels.shape[1]
     _f32(sims), _f32(boxes), _f32(tboxes), _f32(costT)
     assert labels.dtype == torch.int64 and num_targets.dtype == torch.int32 and status.dtype == torch.int32
     check(lib().owl_matcher_cost(_vp(sims), _vp(boxes), _vp(labels), _vp(tboxes), _vp(num_targets), _vp(costT), B, P,
-                                 C, Tmax, _vp(status), _sp()), "owl_matcher_cost")
+                                 C, Tmax, _vp(status), ctypes.c_float(cost_class), ctypes.c_float(cost_bbox),
+                                 ctypes.c_float(cost_giou), _sp()), "owl_matcher_cost")
     return costT
 
 

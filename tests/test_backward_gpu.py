@@ -128,3 +128,43 @@ def test_b32_train_step_grads_vs_reference_golden(golden_dir):
             bad += abs(gn - float(gold["gnorm0." + n])) > 1e-2 * float(gold["gnorm0." + n])
     print("B/32 train-step grads: worst relative error %.2e" % worst)
     assert bad == 0
+
+
+def test_l14_840_backward_vs_autograd():
+    """BASELINE.json configs[3] shape (OWL-ViT-L/14 @ 840 px: 3601 tokens, hidden 1024, 16 heads, ff 4096, embed 768,
+    patch 14), two layers, one image: Engine.backward under the freeze policy (last layer + heads + queries) against
+    torch autograd through the fp32 oracle, same bars as the tiny / B/32 cases (max|diff| <= 3e-2 of the tensor's max;
+    k_proj.bias - a mathematically zero gradient - against the scale of q_proj.bias).  Exercises the long-sequence
+    flavours of the fused attention forward (log-sum-exp output) and backward kernels and every L/14 GEMM shape of the
+    backward pass."""
+    import dataclasses
+    cfg = dataclasses.replace(synth.L14, layers=2)
+    eng, sd, layout = _engine(cfg, seed=3)
+    img = synth.make_images(cfg, 1, seed=7)
+    g = torch.Generator().manual_seed(11)
+    dsims = torch.randn((1, cfg.patches, cfg.n_classes), generator=g) * 1e-3
+    dboxes = torch.randn((1, cfg.patches, 4), generator=g) * 1e-2
+    train = synth.trainable_names(cfg)
+    for n in train:
+        sd[n].requires_grad_(True)
+    rb, rs = oo.forward(sd, cfg, img)
+    ((rs * dsims).sum() + (rb * dboxes).sum()).backward()
+
+    eng.forward(img.cuda())
+    gflat = torch.zeros(layout.n_trainable_padded, device="cuda")
+    eng.backward(dsims.cuda(), dboxes.cuda(), gflat)
+    torch.cuda.synchronize()
+    worst, bad = 0.0, []
+    for n in train:
+        got = _grad_of(layout, gflat, n).cpu()
+        ref = sd[n].grad
+        scale = float(ref.abs().max())
+        if "k_proj.bias" in n:
+            scale = float(sd[n.replace("k_proj", "q_proj")].grad.abs().max())
+        err = float((got - ref).abs().max())
+        worst = max(worst, err / max(scale, 1e-12))
+        tol = 8e-2 if ("q_proj" in n or "k_proj" in n) else 3e-2
+        if err > tol * scale + 1e-9:
+            bad.append((n, err, scale))
+    print("L/14@840 (2 layers) backward: worst relative error %.2e" % worst)
+    assert not bad, bad

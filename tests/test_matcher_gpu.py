@@ -186,3 +186,32 @@ def test_image_without_targets():
         assert np.array_equal(np.isnan(got), np.isnan(ref)), (b, got, ref)
         np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-6, equal_nan=True)
     assert np.isfinite(out["losses_per_image"][[0, 1, 3], :4].numpy()).all()
+
+
+def test_matcher_cost_weights_like_reference_signature():
+    """`HungarianMatcher(n_classes, cost_class, cost_bbox, cost_giou)` (reference src/matcher.py:55-60): other weights
+    than the reference's own 1 / 1 / 1 are honoured - DETR's 1 / 5 / 2 here - with the same product / sum rounding
+    order as the torch expression at src/matcher.py:127-131.  Cost within 1 ulp of the oracle, assignment exact."""
+    from src.matcher import HungarianMatcher
+    from owl_vit_object_detection_b200 import ops
+    T, n = 20, 4
+    sims, pred, lab, tgt = synth.make_matcher_inputs(n, T, seed=9)
+    wc, wb, wg = 1.0, 5.0, 2.0
+    costT = torch.zeros((n, T, 576), device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nt = torch.full((n,), T, dtype=torch.int32, device="cuda")
+    ops.matcher_cost(sims.cuda(), pred.cuda(), lab.cuda(), tgt.cuda(), nt, costT, status, wc, wb, wg)
+    m = HungarianMatcher(80, cost_class=wc, cost_bbox=wb, cost_giou=wg)
+    _, indices, _ = m({"pred_logits": sims.cuda(), "pred_boxes": pred.cuda()},
+                      [{"labels": lab[b].cuda(), "boxes": tgt[b].cuda()} for b in range(n)])
+    for b in range(n):
+        ref = mo.cost_matrix(sims[b], pred[b], lab[b], tgt[b], wc, wb, wg)
+        d = (costT[b].cpu().t() - ref).abs()
+        assert float(d.max()) <= 2e-6 and float((d == 0).float().mean()) >= 0.98, (float(d.max()), float((d == 0).float().mean()))
+        rows, cols = mo.lsap(ref.numpy())
+        assert np.array_equal(indices[b][0].numpy(), rows) and np.array_equal(indices[b][1].numpy(), cols)
+    # and the default weights stay bit-identical to the (l1 - p) - giou form the golden fixtures pin
+    c1 = torch.zeros_like(costT)
+    ops.matcher_cost(sims.cuda(), pred.cuda(), lab.cuda(), tgt.cuda(), nt, c1, status)
+    ref1 = torch.stack([mo.cost_matrix(sims[b], pred[b], lab[b], tgt[b]) for b in range(n)])
+    assert float(((c1.cpu().transpose(1, 2) - ref1) == 0).float().mean()) >= 0.99
