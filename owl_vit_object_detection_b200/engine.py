@@ -304,13 +304,18 @@ class Engine:
         ops.gemm(dy16, x16, dw, M=n_out, N=n_in, K=rows, a_mn=True, b_mn=True, a_ld=dy16.stride(0),
                  b_ld=x16.stride(0), ldo=n_in, split_k=split, out_mode=2, alpha_dev=gscale[1:])
 
-    def backward(self, dsims: torch.Tensor, dboxes: torch.Tensor, grad_flat: torch.Tensor) -> None:
-        """Accumulates d(loss)/d(trainable parameters) into grad_flat (fp32, the trainable tail of the flat
-        layout), given d(loss)/d(pred_sims) [B,P,C] and d(loss)/d(pred_boxes) [B,P,4] of the LAST forward."""
-        with torch.cuda.device(self.device):
-            self._backward(dsims, dboxes, grad_flat)
+    def grad_buckets(self):
+        """See ParamLayout.grad_buckets: the ranges `backward(..., on_ready=)` reports, in completion order."""
+        return self.layout.grad_buckets()
 
-    def _backward(self, dsims: torch.Tensor, dboxes: torch.Tensor, grad_flat: torch.Tensor) -> None:
+    def backward(self, dsims: torch.Tensor, dboxes: torch.Tensor, grad_flat: torch.Tensor, on_ready=None) -> None:
+        """Accumulates d(loss)/d(trainable parameters) into grad_flat (fp32, the trainable tail of the flat
+        layout), given d(loss)/d(pred_sims) [B,P,C] and d(loss)/d(pred_boxes) [B,P,4] of the LAST forward.
+        `on_ready(i)` is called right after the kernels that complete `grad_buckets()[i]` have been enqueued."""
+        with torch.cuda.device(self.device):
+            self._backward(dsims, dboxes, grad_flat, on_ready)
+
+    def _backward(self, dsims: torch.Tensor, dboxes: torch.Tensor, grad_flat: torch.Tensor, on_ready=None) -> None:
         cfg, L = self.cfg, self.layout
         B = dsims.shape[0]
         ws = self.workspace(B)
@@ -368,6 +373,9 @@ class Engine:
         ops.layernorm_bwd(ws.x_out, bw.dcl, self.p32(g1n), gview(g1n), gview(b1n), rows=B, D=D, eps=eps, gscale=gs,
                           dx=bw.dx_out, x_stride=S * D, dx_stride=S * D)                       # CLS rows
 
+        if on_ready is not None:
+            on_ready(0)
+
         # ---- last encoder layer (HF:490-511), MLP half
         p = f"backbone.encoder.layers.{cfg.layers - 1}."
         ops.cast_f16(bw.dx_out, bw.g16)
@@ -381,6 +389,9 @@ class Engine:
         ops.layernorm_bwd(ws.x_mid, bw.dh32, self.p32(p + "layer_norm2.weight"), gview(p + "layer_norm2.weight"),
                           gview(p + "layer_norm2.bias"), rows=M, D=D, eps=eps, gscale=gs, dx=bw.dx_mid,
                           dx_add=bw.dx_out)
+
+        if on_ready is not None:
+            on_ready(1)
 
         # ---- attention half
         ops.cast_f16(bw.dx_mid, bw.g16)
@@ -401,3 +412,5 @@ class Engine:
         ops.gemm(dqkv, self.flat16[lo:hi].view(3 * D, D), bw.dh32, M=M, N=D, K=3 * D, b_mn=True)
         ops.layernorm_bwd(ws.x, bw.dh32, self.p32(p + "layer_norm1.weight"), gview(p + "layer_norm1.weight"),
                           gview(p + "layer_norm1.bias"), rows=M, D=D, eps=eps, gscale=gs)
+        if on_ready is not None:
+            on_ready(2)

@@ -91,6 +91,18 @@ class ParamLayout:
         """[begin, end) element range covering tensors first..last (which must be adjacent)."""
         return self.offsets[first], self.offsets[last] + self._numel(last)
 
+    def grad_buckets(self) -> List[Tuple[int, int]]:
+        """Three contiguous element ranges of the flat gradient buffer (offsets relative to the trainable tail) that
+        tile it, in the order the backward pass COMPLETES them, so a data-parallel driver can reduce one range while
+        the kernels of the next still run: heads + both post layer norms; the MLP half of the last layer (fc1, fc2,
+        layer_norm2); the attention half + layer_norm1 + the query bank."""
+        p = f"backbone.encoder.layers.{self.cfg.layers - 1}."
+        t0 = self.train_begin
+        a = self.offsets["backbone.post_layernorm.weight"] - t0
+        b = self.offsets[p + "mlp.fc1.weight"] - t0
+        assert 0 < b < a <= self.n_trainable_padded and self.offsets["queries"] == t0, "unexpected trainable layout"
+        return [(a, self.n_trainable_padded), (b, a), (0, b)]
+
     def pack(self, sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
         flat = torch.zeros(self.total, dtype=torch.float32, device=device)
         for n in self.shapes:

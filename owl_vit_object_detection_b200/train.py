@@ -41,6 +41,9 @@ class TrainStep:
                 boxes=torch.zeros((batch, max_targets, 4), dtype=torch.float32, device=dev),
                 nt=torch.zeros((batch,), dtype=torch.int32, device=dev)))   # no targets until load()
         self.losses = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in range(n_input_slots)]
+        self._ones4 = torch.ones(4, dtype=torch.float32, device=dev)
+        self._dsims = torch.zeros((batch, cfg.patches, cfg.n_classes), dtype=torch.float32, device=dev)
+        self._dboxes = torch.zeros((batch, cfg.patches, 4), dtype=torch.float32, device=dev)
         self.host_losses = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(n_input_slots)]
         self.read_done = [torch.cuda.Event() for _ in range(n_input_slots)]
         self.copy_stream = torch.cuda.Stream(device=dev)
@@ -53,6 +56,9 @@ class TrainStep:
         if dist.is_available() and dist.is_initialized():
             self._world = dist.get_world_size(group)
         optimizer.grad_mul = 1.0 / self._world
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self._buckets = model.engine.grad_buckets()
+        self._one_graph = True          # N > 1: collectives captured inside the step graph (falls back if capture fails)
         self._next_load = 0
         self._next_run = 0
         self._results_read = 0
@@ -76,12 +82,43 @@ class TrainStep:
 
     # ------------------------------------------------------------------ the step
     def _fwd_bwd(self, slot: int) -> None:
+        """reference main.py:74-90 (zero_grad, forward, criterion, backward) as a straight kernel sequence: the same
+        Engine / matcher / loss entry points `OwlViT.forward`, `PushPullLoss.forward` and autograd's backward reach,
+        without the autograd glue between them (no loss adds, no `stack`, no ones / zeros tensors for the graph)."""
+        from . import ops
         s = self.slots[slot]
-        self.optimizer.zero_grad(set_to_none=False)
-        boxes, _, sims, _ = self.model(s["image"])
-        l = self.criterion(sims, s["labels"], boxes, s["boxes"], num_targets=s["nt"])
-        (l["loss_ce"] + l["loss_bg"] + l["loss_bbox"] + l["loss_giou"]).backward()
-        self.losses[slot].copy_(torch.stack([l["loss_ce"], l["loss_bg"], l["loss_bbox"], l["loss_giou"]]).detach())
+        model, crit = self.model, self.criterion
+        eng = model.engine
+        model._check_policy()
+        model.zero_grad(set_to_none=False)                      # the backward kernels accumulate into flat_grad
+        boxes, sims = eng.forward(s["image"], save_for_backward=True)
+        lab, box, nt = s["labels"], s["boxes"], s["nt"]
+        if crit.scales is not None and crit.scales.device != sims.device:
+            crit.scales = crit.scales.to(sims.device)
+        buf = crit.matcher.assign(sims, boxes, lab, box, nt)
+        ops.match_loss(sims, boxes, lab, box, nt, buf.match, crit.scales, crit.background_label,
+                       tc_matched=buf.tc_matched, tc_final=buf.tc_final, pred_sorted=buf.pred_sorted,
+                       tgt_sorted=buf.tgt_sorted, losses_per_image=buf.losses_per_image, losses_mean4=self.losses[slot],
+                       dsims_unit=buf.dsims_unit, dl1=buf.dl1, dgiou=buf.dgiou)
+        # d(loss_ce + loss_bg + loss_bbox + loss_giou) / d(each loss) = 1   (reference main.py:84-90)
+        ops.loss_backward(buf.dsims_unit, buf.tc_final, buf.match, buf.dl1, buf.dgiou, self._ones4,
+                          crit.background_label, self._dsims, self._dboxes)
+        inside = self._world > 1 and (self._one_graph or not self.use_graph)
+        eng.backward(self._dsims, self._dboxes, model.flat_grad, on_ready=self._reduce_bucket if inside else None)
+        if inside:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)     # join: every bucket is reduced
+
+    def _reduce_bucket(self, i: int) -> None:
+        """Data parallelism: all-reduce (sum; the 1/world is folded into the AdamW kernel) of gradient
+        bucket i on the communication stream, as soon as the backward kernels that complete it are enqueued - the
+        reduction of the heads' and the MLP's gradients runs under the kernels of the rest of the backward pass, only
+        the last bucket (attention projections, 27 % of the bytes) is exposed.  Inside a graph capture the side stream
+        forks from and joins the capturing stream, so the collectives become nodes of the step's ONE graph."""
+        import torch.distributed as dist
+        lo, hi = self._buckets[i]
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.model.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
 
     def _capture(self, fn):
         cur = torch.cuda.current_stream()
@@ -91,7 +128,8 @@ class TrainStep:
             fn()                                     # warm-up: allocates workspaces, sets kernel attributes
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
+            # thread_local: other threads of the process (the NCCL watchdog) may call CUDA APIs during the capture
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
                 fn()
         cur.wait_stream(side)
         return g
@@ -102,15 +140,26 @@ class TrainStep:
             return
         state = (self.model.flat_params.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
                  self.optimizer.state.clone())
-        if self._world == 1:
-            # single GPU: nothing sits between the backward and the optimizer, so the whole step is one graph
-            def whole(i):
-                self._fwd_bwd(i)
-                self.optimizer.step()
-            for i in range(len(self.slots)):
-                if self._fwdbwd[i] is None:
-                    self._fwdbwd[i] = self._capture(lambda i=i: whole(i))
-        else:
+        def whole(i):
+            self._fwd_bwd(i)
+            self.optimizer.step()
+        if self._world == 1 or self._one_graph:
+            # the whole step is ONE graph: on a single GPU nothing sits between the backward and the optimizer; under
+            # data parallelism the bucketed all-reduces are captured on a forked stream inside the same graph
+            try:
+                for i in range(len(self.slots)):
+                    if self._fwdbwd[i] is None:
+                        self._fwdbwd[i] = self._capture(lambda i=i: whole(i))
+            except Exception as e:
+                if self._world == 1:
+                    raise
+                import warnings
+                warnings.warn(f"capturing the collectives into the step graph failed ({e!r}); using two graphs around "
+                              "an eager all-reduce")
+                torch.cuda.synchronize()
+                self._one_graph = False
+                self._fwdbwd = [None] * len(self.slots)
+        if self._world > 1 and not self._one_graph:
             for i in range(len(self.slots)):
                 if self._fwdbwd[i] is None:
                     self._fwdbwd[i] = self._capture(lambda i=i: self._fwd_bwd(i))
@@ -128,6 +177,9 @@ class TrainStep:
             return "eager launches"
         if self._world == 1:
             return "one CUDA-graph replay per step (fwd + loss + bwd + AdamW)"
+        if self._one_graph:
+            return ("one CUDA-graph replay per step (fwd + loss + bwd + 3 bucketed NCCL all-reduces on a forked stream, "
+                    "overlapped with the rest of the backward + AdamW)")
         return "two CUDA-graph replays per step (fwd+loss+bwd, AdamW) around the NCCL all-reduce"
 
     def result(self, slot: int):
@@ -151,11 +203,10 @@ class TrainStep:
         else:
             self._fwd_bwd(slot)
         self.consumed[slot].record(cur)
-        if self._world > 1:
-            self.model.allreduce_grads(self.group)
         if not self.use_graph:
-            self.optimizer.step()
-        elif self._world > 1:
+            self.optimizer.step()                      # (_fwd_bwd already reduced the buckets)
+        elif self._world > 1 and not self._one_graph:
+            self.model.allreduce_grads(self.group)     # fallback: eager all-reduce between two graph replays
             self._opt_graph.replay()
         if readback:
             self.host_losses[slot].copy_(self.losses[slot], non_blocking=True)

@@ -106,6 +106,14 @@ assert torch.equal(model.flat_grad, expect), "all-reduce(sum) over the flat grad
 p = model._param("box_head.dense2.bias")
 o = model.layout.offsets["box_head.dense2.bias"] - model.layout.train_begin
 assert torch.equal(p.grad, expect[o:o + 4])
+# the bucketed reduction TrainStep overlaps with the backward pass: three ranges, in completion order, tile the buffer
+buckets = model.layout.grad_buckets()
+assert sorted(buckets) == [(buckets[2][0], buckets[2][1]), (buckets[1][0], buckets[1][1]), (buckets[0][0], buckets[0][1])]
+assert buckets[2][0] == 0 and buckets[2][1] == buckets[1][0] and buckets[1][1] == buckets[0][0] and buckets[0][1] == g.numel()
+g.copy_(torch.arange(g.numel(), dtype=torch.float32) * (rank + 1))
+for lo, hi in buckets:
+    dist.all_reduce(model.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
+assert torch.equal(model.flat_grad, expect), "bucket by bucket == one all-reduce"
 dist.destroy_process_group()
 sys.stdout.write("rank " + str(rank) + " ok\n")
 """
