@@ -520,6 +520,7 @@ def time_layer_kernels(eng, ws, cfg, B, reps=4):
     x0 = ws.x.clone()          # a real residual-stream state (input of the last layer of the last step)
     for rep in range(reps + 1):
         ws.x.copy_(x0)
+        torch.cuda._sleep(8_000_000)      # ~4 ms spin kernel: the host enqueues the whole sweep behind it
         evs = []
         for i in range(cfg.layers):
             p = f"backbone.encoder.layers.{i}."
