@@ -780,7 +780,13 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the step graphs hold captured NCCL kernels: tearing the communicator down underneath them can block at
+        # interpreter exit, so every rank synchronises and leaves without running destructors
+        sys.stdout.flush()
+        sys.stderr.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

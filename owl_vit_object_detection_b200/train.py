@@ -24,7 +24,7 @@ from .model import FusedAdamW, OwlViT
 class TrainStep:
     def __init__(self, model: OwlViT, criterion: PushPullLoss, optimizer: FusedAdamW, batch: int,
                  max_targets: int = 100, use_graph: bool = True, n_input_slots: int = 2, group=None,
-                 raw_u8: bool = False):
+                 raw_u8: bool = False, world: Optional[int] = None):
         """raw_u8: the input slots hold raw RGB bytes [B,IS,IS,3] (what a decoder produces; the reference's CPU
         rescale + normalise, src/dataset.py:64-71, then happens inside the patch gather on the device) instead of
         the reference's fp32 `pixel_values` [B,3,IS,IS]: a quarter of the host-to-device bytes per step."""
@@ -53,11 +53,19 @@ class TrainStep:
         self._opt_graph = None
         self._world = 1
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
+        if world is not None:
+            self._world = world         # tests: a single-process reference inside a distributed run
+        elif dist.is_available() and dist.is_initialized():
             self._world = dist.get_world_size(group)
         optimizer.grad_mul = 1.0 / self._world
         self.comm_stream = torch.cuda.Stream(device=dev)
         self._buckets = model.engine.grad_buckets()
+        import os
+        # Default: ONE all-reduce of the whole flat buffer after the backward pass, inside the step graph.  OWL_DP_BUCKETS=3
+        # reduces three buckets on a forked stream as the backward pass completes them; measured SLOWER on 2 x B200
+        # (3.641 vs 3.623 ms per step; single GPU 3.50): the NCCL kernels take SMs away from the persistent GEMM grids
+        # (one CTA per SM, static tile schedule), whose tail then waits for the evicted CTAs.
+        self._bucketed = os.environ.get("OWL_DP_BUCKETS", "1") == "3"
         self._one_graph = True          # N > 1: collectives captured inside the step graph (falls back if capture fails)
         self._next_load = 0
         self._next_run = 0
@@ -104,9 +112,12 @@ class TrainStep:
         ops.loss_backward(buf.dsims_unit, buf.tc_final, buf.match, buf.dl1, buf.dgiou, self._ones4,
                           crit.background_label, self._dsims, self._dboxes)
         inside = self._world > 1 and (self._one_graph or not self.use_graph)
-        eng.backward(self._dsims, self._dboxes, model.flat_grad, on_ready=self._reduce_bucket if inside else None)
-        if inside:
+        eng.backward(self._dsims, self._dboxes, model.flat_grad,
+                     on_ready=self._reduce_bucket if (inside and self._bucketed) else None)
+        if inside and self._bucketed:
             torch.cuda.current_stream().wait_stream(self.comm_stream)     # join: every bucket is reduced
+        elif inside:
+            model.allreduce_grads(self.group)
 
     def _reduce_bucket(self, i: int) -> None:
         """Data parallelism: all-reduce (sum; the 1/world is folded into the AdamW kernel) of gradient
@@ -178,6 +189,8 @@ class TrainStep:
         if self._world == 1:
             return "one CUDA-graph replay per step (fwd + loss + bwd + AdamW)"
         if self._one_graph:
+            if not self._bucketed:
+                return "one CUDA-graph replay per step (fwd + loss + bwd + one NCCL all-reduce of the flat grad buffer + AdamW)"
             return ("one CUDA-graph replay per step (fwd + loss + bwd + 3 bucketed NCCL all-reduces on a forked stream, "
                     "overlapped with the rest of the backward + AdamW)")
         return "two CUDA-graph replays per step (fwd+loss+bwd, AdamW) around the NCCL all-reduce"
