@@ -14,9 +14,9 @@ sd = synth.make_weights(cfg, seed=0)
 model = OwlViT({k: v for k, v in sd.items() if k != "queries"}, sd["queries"], cfg=cfg, device="cuda")
 crit = PushPullLoss(cfg.n_classes, synth.make_class_scales(cfg).cuda())
 opt = FusedAdamW(model, lr=3e-6, weight_decay=0.1)
-step = TrainStep(model, crit, opt, batch=B, use_graph=False, n_input_slots=1)
+step = TrainStep(model, crit, opt, batch=B, use_graph=False, n_input_slots=1, raw_u8=True)
 lab, box, nt = synth.make_targets(cfg, B, seed=200)
-step.load(synth.make_images(cfg, B, seed=100), lab, box, nt, slot=0)
+step.load(synth.make_images_u8(cfg, B, seed=100), lab, box, nt, slot=0)
 torch.cuda.synchronize()
 for i in range(steps):
     l0 = _lib.KERNEL_LAUNCHES
