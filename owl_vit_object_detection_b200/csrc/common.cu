@@ -92,7 +92,7 @@ int num_sms() {
 }  // namespace owl
 
 extern "C" const char* owl_last_error(void) { return owl::g_err; }
-extern "C" int owl_abi_version(void) { return 4; }
+extern "C" int owl_abi_version(void) { return 5; }
 
 extern "C" int owl_l2_persist(const void* base, long long bytes, float hit_ratio) {
   using namespace owl;

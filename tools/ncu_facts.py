@@ -1,20 +1,15 @@
-"""profiles/ncu_facts.json from ncu --set full captures (dev tool): ncu_facts.py gemm.ncu-rep flash.ncu-rep"""
-import csv, json, os, subprocess, sys
-def rows(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    r = list(csv.reader(out.splitlines()))
-    return [dict(zip(r[0], x)) for x in r[2:]], dict(zip(r[0], r[1]))
-def nbytes(d, u, k):
-    v = float(d[k].replace(",", ""))
-    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[k]]
-facts = {"source": "ncu --set full --clock-control none, batch 16 (profiles/r01_ncu_full_*.txt)"}
-g, gu = rows(sys.argv[1])
-d = [x for x in g if "EpiF16<(int)1>" in x["Kernel Name"] or "EpiF16<1>" in x["Kernel Name"]][0]
-facts["fc1_gemm_dram_bytes"] = nbytes(d, gu, "dram__bytes_read.sum") + nbytes(d, gu, "dram__bytes_write.sum")
-facts["fc1_gemm_tensor_pipe_pct"] = float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"])
-f, fu = rows(sys.argv[2])
-d = [x for x in f if "flash_attn" in x["Kernel Name"]][0]
-facts["flash_attn_dram_bytes"] = nbytes(d, fu, "dram__bytes_read.sum") + nbytes(d, fu, "dram__bytes_write.sum")
-facts["flash_attn_tensor_pipe_pct"] = float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"])
-json.dump(facts, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_facts.json"), "w"), indent=1)
-print(facts)
+"""profiles/ncu_facts.json from the text summaries of the `ncu --set full` captures under profiles/ (dev tool)."""
+import json, os, re
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+facts = {"source": "ncu --set full --clock-control none, one launch inside an eager step at batch 16 (profiles/r02_ncu_full_*.txt)"}
+for key, name in (("fc2_gemm", "fc2"), ("fc1_gemm", "fc1"), ("qkv_gemm", "qkv"), ("out_proj_gemm", "out_proj"), ("flash_attn", "flash")):
+    txt = open(os.path.join(ROOT, "profiles", f"r02_ncu_full_{name}.txt")).read()
+    def val(metric):
+        m = re.search(re.escape(metric) + r": ([\d.,]+) (\S*)", txt)
+        v = float(m.group(1).replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(2), 1)
+    facts[key + "_dram_bytes"] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+    facts[key + "_tensor_pipe_pct"] = val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+    facts[key + "_ncu_us"] = val("gpu__time_duration.sum")
+json.dump(facts, open(os.path.join(ROOT, "profiles", "ncu_facts.json"), "w"), indent=1)
+print(json.dumps(facts, indent=1))
