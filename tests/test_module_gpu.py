@@ -349,3 +349,36 @@ def test_matcher_flags_out_of_range_labels_and_counts():
     m({"pred_logits": sims, "pred_boxes": boxes}, [{"labels": torch.tensor([1, 7]).cuda(), "boxes": tb}])
     with pytest.raises(IndexError):
         m({"pred_logits": sims, "pred_boxes": boxes}, [{"labels": torch.tensor([1, 8]).cuda(), "boxes": tb}])
+
+
+def test_trainstep_raw_uint8_slots_equal_fp32_slots():
+    """`TrainStep(raw_u8=True)` (raw RGB bytes in the input slots, rescale + normalise fused into the patch gather) must
+    produce exactly the losses and parameters of the fp32 path fed with the reference's preprocessing of the same
+    bytes (oracle: preprocess_oracle, pinned to PIL fixtures; at the model's resolution the resize is the identity)."""
+    from oracle import preprocess_oracle as pre   # checker only
+    from src.losses import PushPullLoss
+    from src.models import FusedAdamW
+    from owl_vit_object_detection_b200.train import TrainStep
+    cfg = synth.TINY
+    B = 2
+    raw = synth.make_images_u8(cfg, B, seed=31)
+    f32 = torch.from_numpy(np.stack([pre.preprocess(im.numpy(), cfg.image_size) for im in raw]))
+    lab, box, nt = synth.make_targets(cfg, B, seed=32, max_t=8)
+    scales = synth.make_class_scales(cfg).cuda()
+
+    def drive(raw_u8, img):
+        model, _ = _model(cfg)
+        step = TrainStep(model, PushPullLoss(cfg.n_classes, scales), FusedAdamW(model, lr=1e-3, weight_decay=0.1),
+                         batch=B, max_targets=lab.shape[1], n_input_slots=1, raw_u8=raw_u8)
+        step.load(img.pin_memory(), lab.pin_memory(), box.pin_memory(), nt.pin_memory(), slot=0)
+        torch.cuda.synchronize()
+        step.warmup()
+        out = [step.run(slot=0).clone() for _ in range(2)]
+        torch.cuda.synchronize()
+        return torch.stack(out).cpu(), model.flat_params.detach().cpu()
+
+    l_u8, p_u8 = drive(True, raw)
+    l_f32, p_f32 = drive(False, f32)
+    assert torch.equal(l_u8[0], l_f32[0]), "same patch rows -> same first-step losses, bit for bit"
+    np.testing.assert_allclose(l_u8.numpy(), l_f32.numpy(), rtol=2e-3)
+    np.testing.assert_allclose(p_u8.numpy(), p_f32.numpy(), rtol=0, atol=2e-4)
