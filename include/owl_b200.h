@@ -232,6 +232,13 @@ int owl_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_
               float lr, float beta1, float beta2, float eps, float weight_decay, float* state, float grad_mul,
               void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (the reference has no distributed code).  Two-shot all-reduce (sum) of a
+ * fp32 buffer that lives in symmetric memory, through the NVSwitch: rank r reduces slice r with multimem.ld_reduce on
+ * the buffer's MULTICAST address and broadcasts the result with multimem.st.  The caller brackets the call with
+ * cross-rank barriers on the same stream (every rank's buffer complete before, every slice landed after). */
+int owl_allreduce_multimem(float* multicast_ptr, long long n, int rank, int world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

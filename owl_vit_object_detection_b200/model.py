@@ -119,6 +119,7 @@ class OwlViT(nn.Module):
         device = torch.device(device) if device is not None else query_bank.device
         self._flat = self.layout.pack(sd, device)
         self._flat_grad: Optional[torch.Tensor] = None
+        self._symm_grad = None          # collective.SymmetricGrad once use_symmetric_grads() succeeded
         self._engine: Optional[Engine] = None
         self._anchor = None
         self._pre = None            # DevicePreprocessor, created on the first uint8 input
@@ -155,6 +156,7 @@ class OwlViT(nn.Module):
         if moved:
             self._engine = None
             self._flat_grad = None
+            self._symm_grad = None
             self._anchor = None
             for name in self._names:
                 p = self._param(name)
@@ -226,11 +228,30 @@ class OwlViT(nn.Module):
             for n in trainable_names(self.cfg):
                 self._param(n).grad = None
 
+    def use_symmetric_grads(self, group=None) -> bool:
+        """Move the flat gradient buffer into symmetric memory so that `allreduce_grads` can reduce it inside the
+        NVSwitch (collective.SymmetricGrad).  Returns False (and changes nothing) without multicast support.  Call
+        once, on every rank, before the first backward."""
+        from .collective import SymmetricGrad
+        sg = SymmetricGrad.create(self.layout.n_trainable_padded, self._flat.device, group)
+        if sg is None:
+            return False
+        self._symm_grad = sg
+        self._flat_grad = sg.buf
+        for n in trainable_names(self.cfg):
+            self._param(n).grad = None          # re-pointed at the new buffer by the next backward
+        return True
+
     def allreduce_grads(self, group=None) -> None:
-        """Data-parallel gradient sync: ONE NCCL all-reduce over the flat fp32 gradient buffer.
-        The 1/world averaging is folded into the optimizer step (FusedAdamW(grad_mul=1/world))."""
+        """Data-parallel gradient sync over the flat fp32 gradient buffer: the in-switch multimem
+        all-reduce when the buffer is symmetric (`use_symmetric_grads`), else ONE NCCL all-reduce.  The 1/world
+        averaging is folded into the optimizer step (FusedAdamW(grad_mul=1/world))."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        if getattr(self, "_symm_grad", None) is not None and self._flat_grad is self._symm_grad.buf:
+            self._symm_grad.all_reduce()
+        else:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
 
     # ------------------------------------------------------------------ reference src/models.py:98-119

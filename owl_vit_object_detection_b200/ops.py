@@ -349,3 +349,9 @@ def adamw(params, grads, exp_avg, exp_avg_sq, params16, *, lr: float, beta1: flo
     check(lib().owl_adamw(_vp(params), _vp(grads), _vp(exp_avg), _vp(exp_avg_sq), _vp(params16), _ll(n), _fl(lr),
                           _fl(beta1), _fl(beta2), _fl(eps), _fl(weight_decay), _vp(state), _fl(grad_mul), _sp()),
           "owl_adamw", kernels=2)
+
+
+def allreduce_multimem(multicast_ptr: int, n: int, rank: int, world: int):
+    """In-switch all-reduce (sum) of a symmetric fp32 buffer addressed through its multicast pointer
+    (owl_allreduce_multimem); the caller issues the cross-rank barriers around it."""
+    check(lib().owl_allreduce_multimem(ctypes.c_void_p(multicast_ptr), _ll(n), rank, world, _sp()), "owl_allreduce_multimem")

@@ -59,6 +59,15 @@ class TrainStep:
             self._world = dist.get_world_size(group)
         optimizer.grad_mul = 1.0 / self._world
         self.comm_stream = torch.cuda.Stream(device=dev)
+        import os as _os
+        # N > 1: reduce the gradients inside the NVSwitch when the platform has multicast support (OWL_DP_MULTIMEM=0
+        # keeps NCCL); must happen before the first backward so that every .grad view points into the symmetric buffer
+        # (measured, 35.2 MB: 2 GPUs multimem 121 us vs NCCL 85 us - every byte, the rank's own included, crosses the
+        # switch; 8 GPUs: see DESIGN.md §6 - so the default is multimem from 4 ranks up, OWL_DP_MULTIMEM=1 forces it)
+        self.multimem = False
+        want = _os.environ.get("OWL_DP_MULTIMEM", "auto")
+        if self._world > 1 and world is None and (want == "1" or (want == "auto" and self._world >= 4)):
+            self.multimem = model.use_symmetric_grads(group)
         self._buckets = model.engine.grad_buckets()
         import os
         # Default: ONE all-reduce of the whole flat buffer after the backward pass, inside the step graph.  OWL_DP_BUCKETS=3
@@ -189,6 +198,9 @@ class TrainStep:
         if self._world == 1:
             return "one CUDA-graph replay per step (fwd + loss + bwd + AdamW)"
         if self._one_graph:
+            if self.multimem:
+                return ("one CUDA-graph replay per step (fwd + loss + bwd + in-switch multimem all-reduce of the flat grad "
+                        "buffer [own kernel, NVLS] + AdamW)")
             if not self._bucketed:
                 return "one CUDA-graph replay per step (fwd + loss + bwd + one NCCL all-reduce of the flat grad buffer + AdamW)"
             return ("one CUDA-graph replay per step (fwd + loss + bwd + 3 bucketed NCCL all-reduces on a forked stream, "
