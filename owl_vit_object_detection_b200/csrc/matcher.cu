@@ -168,22 +168,39 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
   for (int i = threadIdx.x; i < T; i += COST_THREADS)
     if (!(tbox[i * 4 + 2] >= tbox[i * 4 + 0]) || !(tbox[i * 4 + 3] >= tbox[i * 4 + 1])) atomicOr(status, 1);
 
-  // phase 2: items = (row group of 32 predictions, target); lane = prediction inside the group
-  for (int item = warp; item < 2 * T; item += COST_THREADS / 32) {
-    const int grp = item & 1, t = item >> 1;
+  // phase 2: items = (row group of 32 predictions, target); lane = prediction inside the group.  A warp keeps ONE row
+  // group (the item stride, 8 warps, is even), so its prediction box, that box's area and its probability row are
+  // loop invariants held in registers; only the target changes per item.
+  {
+    const int grp = warp & 1;
     const int row = grp * 32 + lane, p = p0 + row;
     if (p < P) {
       const Box pb = {pbox[row * 4 + 0], pbox[row * 4 + 1], pbox[row * 4 + 2], pbox[row * 4 + 3]};
-      const Box tb = {tbox[t * 4 + 0], tbox[t * 4 + 1], tbox[t * 4 + 2], tbox[t * 4 + 3]};
-      // torch.cdist(p=1): ((|dx0| + |dy0|) + |dx1|) + |dy1|   (reference src/matcher.py:121)
-      const float l1 = fadd(fadd(fadd(fabsf(fsub(pb.x0, tb.x0)), fabsf(fsub(pb.y0, tb.y0))),
-                                 fabsf(fsub(pb.x1, tb.x1))), fabsf(fsub(pb.y1, tb.y1)));
-      const float pr = prob[row * (C + 1) + tlab[t]];
-      const float gi = giou_pair(pb, tb);
-      // (w_bbox * cost_bbox + w_class * cost_class) + w_giou * cost_giou with cost_class = -p, cost_giou = -giou
-      // (src/matcher.py:127-131; every product and sum rounds separately, like the torch ops).  With the reference's
-      // weights (all 1, src/matcher.py:58-60) the products are exact and this is (l1 - p) - giou bit for bit.
-      costT[(1LL * b * Tmax + t) * P + p] = fadd(fadd(fmul(w_bbox, l1), fmul(w_class, -pr)), fmul(w_giou, -gi));
+      const float area1 = fmul(fsub(pb.x1, pb.x0), fsub(pb.y1, pb.y0));          // torchvision box_area(boxes1)
+      const float* prow = prob + row * (C + 1);
+      float* dst = costT + (1LL * b * Tmax) * P + p;
+      for (int t = warp >> 1; t < T; t += COST_THREADS / 64) {
+        const Box tb = {tbox[t * 4 + 0], tbox[t * 4 + 1], tbox[t * 4 + 2], tbox[t * 4 + 3]};
+        // torch.cdist(p=1): ((|dx0| + |dy0|) + |dx1|) + |dy1|   (reference src/matcher.py:121)
+        const float l1 = fadd(fadd(fadd(fabsf(fsub(pb.x0, tb.x0)), fabsf(fsub(pb.y0, tb.y0))),
+                                   fabsf(fsub(pb.x1, tb.x1))), fabsf(fsub(pb.y1, tb.y1)));
+        const float pr = prow[tlab[t]];
+        // reference src/matcher.py:8-21,25-44 (same op order as iou_union / giou_pair above, area1 hoisted)
+        const float area2 = fmul(fsub(tb.x1, tb.x0), fsub(tb.y1, tb.y0));
+        const float iw = fmaxf(fsub(fminf(pb.x1, tb.x1), fmaxf(pb.x0, tb.x0)), 0.0f);
+        const float ih = fmaxf(fsub(fminf(pb.y1, tb.y1), fmaxf(pb.y0, tb.y0)), 0.0f);
+        const float inter = fmul(iw, ih);
+        const float uni = fsub(fadd(area1, area2), inter);
+        const float iou = fdiv(inter, uni);
+        const float cw = fmaxf(fsub(fmaxf(pb.x1, tb.x1), fminf(pb.x0, tb.x0)), 0.0f);
+        const float ch = fmaxf(fsub(fmaxf(pb.y1, tb.y1), fminf(pb.y0, tb.y0)), 0.0f);
+        const float hull = fmul(cw, ch);
+        const float gi = fsub(iou, fdiv(fsub(hull, uni), hull));
+        // (w_bbox * cost_bbox + w_class * cost_class) + w_giou * cost_giou with cost_class = -p, cost_giou = -giou
+        // (src/matcher.py:127-131; every product and sum rounds separately, like the torch ops).  With the reference's
+        // weights (all 1, src/matcher.py:58-60) the products are exact and this is (l1 - p) - giou bit for bit.
+        dst[1LL * t * P] = fadd(fadd(fmul(w_bbox, l1), fmul(w_class, -pr)), fmul(w_giou, -gi));
+      }
     }
   }
 }
