@@ -60,13 +60,16 @@ __device__ __forceinline__ float giou_pair(const Box& a, const Box& b) {
 // =====================================================================================================
 constexpr int COST_ROWS = 64;      // predictions per CTA (two passes of 32 rows x 8 lanes through the softmax)
 constexpr int COST_THREADS = 256;
+#ifndef OWL_COST_MINB
+#define OWL_COST_MINB 5
+#endif
 
 // The kernel is instruction-issue bound (ncu: issue slots 73 % busy, DRAM 21 %: the index-exact arithmetic costs
 // ~4x a fast-math version), so the row length is a template parameter (no dead iterations / predicates) and a CTA
 // covers 64 predictions (the per-CTA target set-up is amortised, and 2 x T (row group, target) items fill the
 // eight warps of the pair phase better than T items do).
 template <int NVEC /* float4 per lane: ceil(C / 32) */, bool VEC /* C % 4 == 0 */>
-__global__ void __launch_bounds__(COST_THREADS)
+__global__ void __launch_bounds__(COST_THREADS, OWL_COST_MINB)
 matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ boxes,
                     const long long* __restrict__ labels, const float* __restrict__ tboxes,
                     const int* __restrict__ num_targets, float* __restrict__ costT, int P, int C, int Tmax,
