@@ -67,6 +67,29 @@ int make_tensor_map_f16(CUtensorMap* out, const void* base, uint64_t inner, uint
   return OWL_OK;
 }
 
+int make_tensor_map_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                        uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return OWL_ERR_DRIVER;
+  }
+  OWL_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p not 16-byte aligned", base);
+  OWL_CHECK_ARG((row_stride * 4) % 16 == 0 && box_inner * 4 <= 128, "tensor map (f32): bad row stride / box");
+  cuuint64_t dims[3] = {inner, rows, 1};
+  cuuint64_t strides[2] = {row_stride * 4, rows * row_stride * 4};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32) failed with CUresult %d", static_cast<int>(r));
+    return OWL_ERR_DRIVER;
+  }
+  return OWL_OK;
+}
+
 static L2Window g_l2_window = {nullptr, 0, 0.f};
 const L2Window& l2_window() { return g_l2_window; }
 

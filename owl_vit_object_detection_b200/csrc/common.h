@@ -40,6 +40,10 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns the (posi
 int make_tensor_map_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches,
                         uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows);
 
+// same for fp32 elements (box_inner * 4 bytes <= 128: one swizzle row)
+int make_tensor_map_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                        uint32_t box_inner, uint32_t box_rows);
+
 int num_sms();
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a process that drives several GPUs has to opt in on

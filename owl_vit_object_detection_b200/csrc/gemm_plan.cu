@@ -149,6 +149,20 @@ int gemm_plan_build(const owl_gemm_args& a, int bn, GemmPlan* plan) {
     auto al32 = [](const void* q, long long ld) { return !q || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld * 4) % 16 == 0); };
     e.vec_ok = al32(a.out, a.ldo) && al32(a.resid, a.ldr) && al32(a.pos, a.ldo) &&
                (a.o_outer_stride * 4) % 16 == 0 && (a.o_head_stride * 4) % 16 == 0;
+    // TMA residual loads + TMA stores: plain store of one [M, N] matrix (no accumulate / atomics / row remap / pos-emb)
+    static const bool tma_off32 = [] { const char* v = getenv("OWL_GEMM_TMA_STORE"); return v && v[0] == '0'; }();
+    e.use_tma = (!tma_off32 && G == 1 && e.vec_ok && a.out_mode == 0 && a.split_k == 1 && a.rows_per_img == 0 && !a.pos &&
+                 a.N % 32 == 0 && (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0)) ? 1 : 0;
+    if (e.use_tma) {
+      rc = make_tensor_map_f32(&e.tm_out, a.out, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M),
+                               static_cast<uint64_t>(a.ldo), 32, 32);
+      if (rc) return rc;
+      if (a.resid) {
+        rc = make_tensor_map_f32(&e.tm_resid, a.resid, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M),
+                                 static_cast<uint64_t>(a.ldr), 32, 32);
+        if (rc) return rc;
+      }
+    }
   } else {
     EpiPool3::Params& e = p.pp;
     e.sims = static_cast<float*>(a.out);

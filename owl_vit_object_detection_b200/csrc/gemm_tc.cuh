@@ -55,13 +55,13 @@ __host__ __device__ constexpr int gemm_stage_bytes(int BN, int CM = 1) { return 
 // share an SM.
 __host__ __device__ constexpr int gemm_num_stages(int BN, int CM = 1, int MINB = 1) {
   const int budget = MINB == 2 ? 64 * 1024
-                               : GEMM_SMEM_LIMIT - gemm_epi_warps(BN) * (GEMM_EPI_STAGE_BYTES + GEMM_EPI_BIAS_BYTES) - 1024 - 256;
+                               : GEMM_SMEM_LIMIT - gemm_epi_warps(BN) * (GEMM_EPI_STAGE_BYTES + GEMM_EPI_BIAS_BYTES) - 1024 - 512;
   const int n = budget / gemm_stage_bytes(BN, CM);
   return n > 8 ? 8 : n;
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int BN, int CM = 1, int MINB = 1) {
   return gemm_num_stages(BN, CM, MINB) * gemm_stage_bytes(BN, CM) +
-         gemm_epi_warps(BN) * (GEMM_EPI_STAGE_BYTES + GEMM_EPI_BIAS_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+         gemm_epi_warps(BN) * (GEMM_EPI_STAGE_BYTES + GEMM_EPI_BIAS_BYTES) + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 __host__ __device__ constexpr int gemm_tmem_cols(int BN) {
   return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -118,7 +118,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* epi_bar = tempty_bar + 2;         // [EPI_WARPS] per epilogue warp: TMA loads into its staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,6 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], EPI_WARPS * CM);
     }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&epi_bar[w], 1);
     fence_barrier_init();
   }
   if constexpr (CM > 1) cluster_sync_all();   // both CTAs are resident with initialised barriers before pair ops
@@ -277,6 +279,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NH = BN / PARTS;
     const uint32_t stage_buf = smem_u32(epi_stage + warp * GEMM_EPI_STAGE_BYTES);
     const uint32_t bias_buf = smem_u32(epi_bias + warp * GEMM_EPI_BIAS_BYTES);
+    uint64_t* ebar = &epi_bar[warp];
+    uint32_t ephase = 0;
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int g = t / tiles_per_g;
@@ -291,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // global operands of the epilogue (bias slice, first residual chunk) are fetched BEFORE waiting for the
       // accumulator, so their latency hides behind the tile's MMAs
       typename Epi::Pre pre;
-      Epi::template prologue<Epi::kSplitColumns ? NH : BN>(ep, pre, g, row0, lane, ncol0, gs.M, gs.N);
+      Epi::template prologue<Epi::kSplitColumns ? NH : BN>(ep, pre, g, row0, lane, ncol0, gs.M, gs.N, stage_buf, ebar);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -301,9 +305,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (gs.debug & 1) {
         // dev: accumulator handed back untouched
       } else if constexpr (Epi::kSplitColumns) {
-        Epi::template run<NH>(ep, pre, taddr + half * NH, stage_buf, bias_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
+        Epi::template run<NH>(ep, pre, taddr + half * NH, stage_buf, bias_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k,
+                              ebar, ephase);
       } else if (half == 0) {
-        Epi::template run<BN>(ep, pre, taddr, stage_buf, bias_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k);
+        Epi::template run<BN>(ep, pre, taddr, stage_buf, bias_buf, g, row0, lane, ncol0, gs.M, gs.N, has_k, ebar, ephase);
       }
       tc_fence_before();
       __syncwarp();
@@ -492,14 +497,14 @@ struct EpiF16 {
   struct Pre { float4 bias; };
   template <int BN>
   static __device__ __forceinline__ void prologue(const Params& p, Pre& pre, int g, int row0, int lane, int n0, int M,
-                                                  int N) {
+                                                  int N, uint32_t, uint64_t*) {
     (void)g; (void)row0; (void)M;
     pre.bias = load_bias_slice<BN>(p.bias, n0, N, lane);
   }
   template <int BN>
   static __device__ __forceinline__ void run(const Params& p, const Pre& pre, uint32_t taddr, uint32_t stage,
                                              uint32_t bias_smem, int g, int row0, int lane, int n0, int M, int Nfull,
-                                             bool has_k) {
+                                             bool has_k, uint64_t*, uint32_t&) {
     const int N = min(Nfull, n0 + BN);  // this warp's column slice ends here
     const int outer = g / p.H, head = g - outer * p.H;
     __half* out = p.out + outer * p.o_sb + head * p.o_sh;
@@ -642,8 +647,20 @@ struct EpiF32 {
     int vec_ok;            // out / resid / pos rows are 16-byte aligned
     float alpha;
     const float* alpha_dev;
+    int use_tma;             // mode 0, one [M, N] matrix, 16-byte aligned rows: TMA residual loads + TMA stores
+    CUtensorMap tm_out;      // [M, N] fp32, box 32 columns x 32 rows, 128-byte swizzle (= the staging tile's layout)
+    CUtensorMap tm_resid;
   };
   struct Pre { float4 bias; float4 add[8]; float4 b4; };
+  // TMA path of the layer GEMMs (out-proj, fc2, fp32 dgrads): the 32 x 32 residual tile of a chunk is loaded by the TMA
+  // unit straight into the warp's swizzled staging tile (the first chunk's while the tile's MMAs still run), every
+  // thread adds its accumulator row + the bias (shared-memory broadcasts) IN PLACE - thread t owns row t, so there is
+  // no transposition, no line phase, no per-row global address arithmetic - and one lane stores the tile with a
+  // bulk-tensor copy (rows past M are zero-filled on the way in and clipped on the way out).
+  template <int BN>
+  static __device__ __forceinline__ bool tma_path(const Params& p, int n0, int N) {
+    return p.use_tma != 0 && n0 + BN <= N;
+  }
   // line phase gather of resid + pos + old output for the 32 x 32 tile at column n (registers only).
   // All loads of a chunk are issued back to back BEFORE anything consumes them: the SM issues in order, so a
   // consumer (or a data-dependent branch) between two loads would expose one full memory latency per load
@@ -756,7 +773,16 @@ struct EpiF32 {
   }
   template <int BN>
   static __device__ __forceinline__ void prologue(const Params& p, Pre& pre, int g, int row0, int lane, int n0, int M,
-                                                  int N) {
+                                                  int N, uint32_t stage, uint64_t* ebar) {
+    if (tma_path<BN>(p, n0, N)) {
+      pre.bias = load_bias_slice<BN>(p.bias, n0, N, lane);
+      if (row0 < M && p.resid != nullptr && lane == 0) {
+        tma_store_wait_read();                 // the previous tile's last store has finished reading the staging tile
+        mbar_arrive_expect_tx(ebar, 4096);
+        tma_load_3d_s(stage, &p.tm_resid, ebar, n0, row0, 0);
+      }
+      return;
+    }
     if (lean<BN>(p, n0, N)) {
       if (row0 < M) {
         const int outer = g / p.H, head = g - outer * p.H;
@@ -773,8 +799,7 @@ struct EpiF32 {
   template <int BN>
   static __device__ __forceinline__ void run(const Params& p, Pre& pre, uint32_t taddr, uint32_t stage,
                                              uint32_t bias_smem, int g, int row0, int lane, int n0, int M, int N,
-                                             bool has_k) {
-    (void)bias_smem;
+                                             bool has_k, uint64_t* ebar, uint32_t& ephase) {
     const int outer = g / p.H, head = g - outer * p.H;
     float* out = p.out + outer * p.o_sb + head * p.o_sh;
     const bool vec_ok = p.vec_ok != 0;
@@ -783,6 +808,58 @@ struct EpiF32 {
     if (!has_k && p.mode != 0) return;  // an empty K slice adds nothing
     const bool has_add = has_addend(p);
     const int sr = lane >> 3, sc = lane & 7;
+    if (tma_path<BN>(p, n0, N)) {
+      const bool with_resid = p.resid != nullptr;
+      if (p.bias) {     // the slice's bias -> shared memory, read back as broadcasts
+        if (lane < BN / 4)
+          sts128(bias_smem + lane * 16, make_uint4(__float_as_uint(pre.bias.x), __float_as_uint(pre.bias.y),
+                                                   __float_as_uint(pre.bias.z), __float_as_uint(pre.bias.w)));
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c > 0 && with_resid && lane == 0) {     // chunk 0's residual tile was requested in the prologue
+          tma_store_wait_read();
+          mbar_arrive_expect_tx(ebar, 4096);
+          tma_load_3d_s(stage, &p.tm_resid, ebar, n0 + c * 32, row0, 0);
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (with_resid) {
+          mbar_wait(ebar, ephase);
+          ephase ^= 1;
+        } else {
+          if (lane == 0) tma_store_wait_read();     // the staging tile is free again
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t sa = stage_addr(stage, lane, q);
+          // same summation order as the line-phase path: (alpha * acc + bias) + residual
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_k)
+            o = make_float4(__uint_as_float(r[4 * q]) * alpha, __uint_as_float(r[4 * q + 1]) * alpha,
+                            __uint_as_float(r[4 * q + 2]) * alpha, __uint_as_float(r[4 * q + 3]) * alpha);
+          if (p.bias) {
+            const uint4 bq = lds128(bias_smem + (c * 8 + q) * 16);
+            o.x += __uint_as_float(bq.x); o.y += __uint_as_float(bq.y); o.z += __uint_as_float(bq.z); o.w += __uint_as_float(bq.w);
+          }
+          if (with_resid) {
+            const uint4 u = lds128(sa);
+            o.x += __uint_as_float(u.x); o.y += __uint_as_float(u.y); o.z += __uint_as_float(u.z); o.w += __uint_as_float(u.w);
+          }
+          sts128(sa, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&p.tm_out, stage, n0 + c * 32, row0, 0);
+          tma_store_commit();
+        }
+      }
+      return;
+    }
     if (lean<BN>(p, n0, N)) {
       float* d0 = out + (long long)(row0 + sr) * p.ldo + n0 + sc * 4;
       const long long step = 4LL * p.ldo;
@@ -899,11 +976,11 @@ struct EpiPool3 {
   };
   struct Pre {};
   template <int BN>
-  static __device__ __forceinline__ void prologue(const Params&, Pre&, int, int, int, int, int, int) {}
+  static __device__ __forceinline__ void prologue(const Params&, Pre&, int, int, int, int, int, int, uint32_t, uint64_t*) {}
   template <int BN>
   static __device__ __forceinline__ void run(const Params& p, const Pre&, uint32_t taddr, uint32_t stage,
                                              uint32_t bias_smem, int g, int row0, int lane, int n0, int M, int N,
-                                             bool has_k) {
+                                             bool has_k, uint64_t*, uint32_t&) {
     (void)g; (void)has_k; (void)stage; (void)bias_smem;
     const int m = row0 + lane;
 #pragma unroll 1

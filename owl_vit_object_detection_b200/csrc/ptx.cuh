@@ -81,6 +81,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// same, destination given as a shared-memory address
+__device__ __forceinline__ void tma_load_3d_s(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                              int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // 3-D tiled store shared -> global (bulk async group of the issuing thread).  The shared-memory tile must be in the
 // tensor map's swizzle layout; elements outside the tensor are clipped by the TMA unit.
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
