@@ -23,6 +23,8 @@ extern "C" {
 #endif
 
 const char* owl_last_error(void);
+/* Zero-fill `bytes` bytes at `ptr` on the stream (cudaMemsetAsync: a memset node inside a captured graph). */
+int owl_zero(void* ptr, long long bytes, void* stream);
 /* ABI version of this header; bumped on any signature change. */
 int owl_abi_version(void);
 

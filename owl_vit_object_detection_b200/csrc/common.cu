@@ -114,6 +114,15 @@ int num_sms() {
 
 }  // namespace owl
 
+// Zero-fill on the stream (a memset node when captured into a CUDA graph): the atomically accumulated buffers of a step
+// (flat gradient buffer, dqn / dcl scratch, matcher status word) are cleared through this, not through framework kernels.
+extern "C" int owl_zero(void* ptr, long long bytes, void* stream) {
+  if (!ptr || bytes < 0) { owl::set_error("owl_zero: bad arguments"); return owl::OWL_ERR_ARG; }
+  if (bytes == 0) return owl::OWL_OK;
+  OWL_CUDA(cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+  return owl::OWL_OK;
+}
+
 extern "C" const char* owl_last_error(void) { return owl::g_err; }
 extern "C" int owl_abi_version(void) { return 5; }
 

@@ -353,7 +353,7 @@ class Engine:
         # ---- class head (reference src/models.py:24-38)
         ops.pool3_bwd(dsims, ws.argmax, gs, bw.dfull)
         ops.gemm(bw.dfull, ws.qn16, bw.den32, M=MP, N=E, K=Q, b_mn=True)                      # d(en) = dfull qn
-        bw.dqn32.zero_()
+        ops.zero(bw.dqn32)
         ops.gemm(bw.dfull, ws.en16, bw.dqn32, M=Q, N=E, K=MP, a_mn=True, b_mn=True, a_ld=Q, b_ld=E, ldo=E,
                  split_k=max(1, min(16, (MP + 511) // 512)), out_mode=2)                       # d(qn) = dfull^T en
         ops.rownorm_bwd(self.p32("queries").view(Q, E), bw.dqn32, gview("queries").view(Q, E), rows=Q, E=E,
@@ -366,7 +366,7 @@ class Engine:
 
         # ---- reference src/models.py:80-86 backward
         g1n, b1n = "backbone.post_layernorm.weight", "backbone.post_layernorm.bias"
-        bw.dcl.zero_()
+        ops.zero(bw.dcl)
         ops.post_fuse_bwd(ws.x_out, ws.ecls, self.p32(g1n), self.p32(b1n), self.p32("post_post_layernorm.weight"),
                           bw.dfeats, bw.dx_out, bw.dcl, gview(g1n), gview(b1n), gview("post_post_layernorm.weight"),
                           gview("post_post_layernorm.bias"), B=B, P=P, D=D, eps=eps, gscale=gs)

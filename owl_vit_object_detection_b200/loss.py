@@ -96,7 +96,7 @@ class HungarianMatcher(nn.Module):
         B, P, C = sims.shape
         buf = self.buffers(B, P, C, lab.shape[1], sims.device)
         buf.generation += 1
-        buf.status.zero_()
+        ops.zero(buf.status)
         with torch.cuda.device(sims.device):
             ops.matcher_cost(sims, boxes, lab, box, nt, buf.costT, buf.status, self.cost_class, self.cost_bbox,
                              self.cost_giou)

@@ -190,6 +190,15 @@ class OwlViT(nn.Module):
                                           device=self._flat.device)
         return self._flat_grad
 
+    @staticmethod
+    def _zero(t: torch.Tensor) -> None:
+        """Clear a (slice of the) gradient buffer: a memset on the stream for device memory (owl_zero), torch otherwise."""
+        if t.is_cuda and t.is_contiguous():
+            from . import ops
+            ops.zero(t)
+        else:
+            t.zero_()
+
     def _check_policy(self) -> None:
         train = set(trainable_names(self.cfg))
         for name in self._names:
@@ -208,14 +217,14 @@ class OwlViT(nn.Module):
         names = [n for n in trainable_names(self.cfg) if self._param(n).requires_grad]
         wholesale = all(self._param(n).grad is None for n in names)
         if wholesale:
-            g.zero_()
+            self._zero(g)
         for n in names:
             p = self._param(n)
             o = L.offsets[n] - L.train_begin
             view = g[o:o + L._numel(n)].view(L.shapes[n])
             if p.grad is None:
                 if not wholesale:
-                    view.zero_()
+                    self._zero(view)
                 p.grad = view
             elif p.grad.data_ptr() != view.data_ptr():
                 raise RuntimeError(f"{n}.grad was replaced by a foreign tensor; use model.zero_grad() or "
@@ -223,7 +232,7 @@ class OwlViT(nn.Module):
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         if self._flat_grad is not None:
-            self._flat_grad.zero_()
+            self._zero(self._flat_grad)
         if set_to_none:
             for n in trainable_names(self.cfg):
                 self._param(n).grad = None

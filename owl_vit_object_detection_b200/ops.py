@@ -195,6 +195,14 @@ def attn_bwd(qkv16: torch.Tensor, dctx16: torch.Tensor, lse: torch.Tensor, delta
     return dqkv16
 
 
+def zero(t: torch.Tensor) -> torch.Tensor:
+    """t[...] = 0 through owl_zero (cudaMemsetAsync on the current stream; no framework kernel)."""
+    assert t.is_cuda and t.is_contiguous()
+    with torch.cuda.device(t.device):
+        check(lib().owl_zero(_vp(t), _ll(t.numel() * t.element_size()), _sp()), "owl_zero", kernels=0)
+    return t
+
+
 def cast_f16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
     _f32(src)
     assert dst.dtype == torch.float16 and dst.numel() == src.numel()
