@@ -203,10 +203,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_img = 2
-    steps = max(1, min(args.steps, 20))          # bounded: ~0.2 s per image per step on 16 cores
+    n_img = 2                                     # one "step" of this arm = the reference's batch-1 loop over 2 images
+    steps = max(1, min(args.steps, 600))          # ~0.22 s per step on 16 host cores: K steps stay within minutes
+    warm = max(1, min(args.warmup, 10))
     t0 = time.time()
-    sec_per_img, cores, kind = reference_cpu_step_time(n_img, iters=steps, warmup=1)
+    sec_per_img, cores, kind = reference_cpu_step_time(n_img, iters=steps, warmup=warm)
     val = 1.0 / sec_per_img
     sample = (f"{steps} timed steps of {n_img} images each (batch-1 loop as reference main.py:70-93: fwd + "
               f"PushPullLoss + bwd + AdamW), fp32 torch CPU, {cores} threads on {cpu_model()}; "
@@ -214,7 +215,7 @@ def run_reference(args):
               f"wall {time.time() - t0:.0f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": sec_per_img * 1e3 * n_img, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": sec_per_img * 1e3 * n_img, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_step": n_img,
                    "note": "CPU arm does not use the GPUs; n_gpus echoes the launch; the reference is batch-1 only"},

@@ -24,6 +24,16 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
+// exp of the softmax numerator (argument <= 0).  The class term cannot be bit-identical to the reference's CPU softmax
+// anyway (Sleef vs CUDA expf, different summation order: SURVEY 8 a.1) and is ~1/80 of the cost, so the 2-ulp
+// ex2.approx form (2 instructions instead of ~10; the kernel is instruction-issue bound, ncu: issue 85 % at T = 10) is
+// used; bench.py checks the resulting assignments of 10 000 images per T against the reference arithmetic every run.
+__device__ __forceinline__ float soft_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 struct Box { float x0, y0, x1, y1; };
 
 // status bits (host raises what the reference would have raised inline): 1 degenerate box (src/matcher.py:34-35),
@@ -141,10 +151,10 @@ matcher_cost_kernel(const float* __restrict__ sims, const float* __restrict__ bo
       for (int k = 0; k < NVEC; ++k) {
         const int c = k * 32 + sub * 4;
         float4& x = v[pass][k];
-        x.x = c < C ? expf(fsub(x.x, m)) : 0.f;
-        x.y = c + 1 < C ? expf(fsub(x.y, m)) : 0.f;
-        x.z = c + 2 < C ? expf(fsub(x.z, m)) : 0.f;
-        x.w = c + 3 < C ? expf(fsub(x.w, m)) : 0.f;
+        x.x = c < C ? soft_exp(fsub(x.x, m)) : 0.f;
+        x.y = c + 1 < C ? soft_exp(fsub(x.y, m)) : 0.f;
+        x.z = c + 2 < C ? soft_exp(fsub(x.z, m)) : 0.f;
+        x.w = c + 3 < C ? soft_exp(fsub(x.w, m)) : 0.f;
         s += (x.x + x.y) + (x.z + x.w);
       }
 #pragma unroll
