@@ -241,6 +241,24 @@ int owl_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_
  * cross-rank barriers on the same stream (every rank's buffer complete before, every slice landed after). */
 int owl_allreduce_multimem(float* multicast_ptr, long long n, int rank, int world, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Query-bank initialisation: reference src/models.py:155-169 runs the HF TEXT tower once over three
+ * prompts per class and keeps `text_embeds` as the learned queries.  The encoder layers reuse owl_layernorm / owl_gemm
+ * (HF:490-511); these four entry points are the text-only pieces.  ids = int64 token ids [N prompts, S tokens]. */
+/* HF:370-373: x[n*S + s, :] = token_embedding[ids[n, s]] + position_embedding[s] (fp32).  An id outside [0, vocab)
+ * (IndexError in nn.Embedding) sets bit 8 of *status (may be NULL) and reads row 0. */
+int owl_text_embed(const long long* ids, const float* tok_emb, const float* pos_emb, float* x, int rows, int S, int D,
+                   int vocab, int* status, void* stream);
+/* HF:379-404 under the mask of HF:661-666: packed q|k|v fp16 [N*S, 3*H*64] -> ctx fp16 [N*S, H*64]; query s sees key j
+ * iff j <= s (causal) and mask[n, j] != 0 (attention_mask as int32, NULL = no padding).  S <= 32, head_dim 64. */
+int owl_text_attn(const void* qkv_f16, const int* mask, void* ctx_f16, int N, int S, int H, int head_dim, float scale,
+                  void* stream);
+/* HF:677-684: final LayerNorm of the end-of-text row of each prompt (first argmax of its ids) -> fp16 [N, D]. */
+int owl_text_pool_ln(const float* x, const long long* ids, const float* gamma, const float* beta, void* out_f16, int N,
+                     int S, int D, float eps, void* stream);
+/* HF:984: out[r, :] = in[r, :] / ||in[r, :]||_2 (fp32; in == out allowed). */
+int owl_l2norm_rows(const float* in, float* out, int rows, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

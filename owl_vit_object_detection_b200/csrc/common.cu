@@ -124,7 +124,7 @@ extern "C" int owl_zero(void* ptr, long long bytes, void* stream) {
 }
 
 extern "C" const char* owl_last_error(void) { return owl::g_err; }
-extern "C" int owl_abi_version(void) { return 5; }
+extern "C" int owl_abi_version(void) { return 6; }
 
 extern "C" int owl_l2_persist(const void* base, long long bytes, float hit_ratio) {
   using namespace owl;

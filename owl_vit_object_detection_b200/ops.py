@@ -363,3 +363,46 @@ def allreduce_multimem(multicast_ptr: int, n: int, rank: int, world: int):
     """In-switch all-reduce (sum) of a symmetric fp32 buffer addressed through its multicast pointer
     (owl_allreduce_multimem); the caller issues the cross-rank barriers around it."""
     check(lib().owl_allreduce_multimem(ctypes.c_void_p(multicast_ptr), _ll(n), rank, world, _sp()), "owl_allreduce_multimem")
+
+
+# ------------------------------------------------------------------------------------------ text tower (row N4)
+def text_embed(ids: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor, x: torch.Tensor, *, S: int,
+               status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """HF:370-373: x[n*S + s] = tok_emb[ids[n, s]] + pos_emb[s] (owl_text_embed)."""
+    assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous()
+    _f32(tok_emb), _f32(pos_emb), _f32(x)
+    rows, D = ids.numel(), tok_emb.shape[1]
+    assert x.numel() == rows * D and pos_emb.shape[0] >= S and pos_emb.shape[1] == D
+    check(lib().owl_text_embed(_vp(ids), _vp(tok_emb), _vp(pos_emb), _vp(x), rows, S, D, int(tok_emb.shape[0]),
+                               _vp(status), _sp()), "owl_text_embed")
+    return x
+
+
+def text_attn(qkv16: torch.Tensor, mask: Optional[torch.Tensor], ctx16: torch.Tensor, *, N: int, S: int, H: int,
+              head_dim: int, scale: float) -> torch.Tensor:
+    """HF:379-404 with the causal + padding mask of the text model (owl_text_attn)."""
+    assert qkv16.dtype == torch.float16 and ctx16.dtype == torch.float16 and qkv16.is_contiguous()
+    assert qkv16.numel() == N * S * 3 * H * head_dim and ctx16.numel() == N * S * H * head_dim
+    if mask is not None:
+        assert mask.is_cuda and mask.dtype == torch.int32 and mask.is_contiguous() and mask.numel() == N * S
+    check(lib().owl_text_attn(_vp(qkv16), _vp(mask), _vp(ctx16), N, S, H, head_dim, ctypes.c_float(scale), _sp()),
+          "owl_text_attn")
+    return ctx16
+
+
+def text_pool_ln(x: torch.Tensor, ids: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out16: torch.Tensor, *,
+                 N: int, S: int, D: int, eps: float) -> torch.Tensor:
+    """HF:677-684: final LayerNorm of each prompt's end-of-text row -> fp16 [N, D] (owl_text_pool_ln)."""
+    _f32(x), _f32(gamma), _f32(beta)
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and out16.dtype == torch.float16
+    check(lib().owl_text_pool_ln(_vp(x), _vp(ids), _vp(gamma), _vp(beta), _vp(out16), N, S, D, ctypes.c_float(eps),
+                                 _sp()), "owl_text_pool_ln")
+    return out16
+
+
+def l2norm_rows(src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """HF:984: rows divided by their L2 norm (owl_l2norm_rows)."""
+    _f32(src), _f32(out)
+    rows, D = src.shape
+    check(lib().owl_l2norm_rows(_vp(src), _vp(out), rows, D, _sp()), "owl_l2norm_rows")
+    return out

@@ -5,6 +5,7 @@ import torch
 
 from owl_vit_object_detection_b200.model import FusedAdamW, OwlViT  # noqa: F401
 from owl_vit_object_detection_b200.synth import trainable_names
+from owl_vit_object_detection_b200.text import text_query_bank
 
 
 class PostProcess:
@@ -47,8 +48,9 @@ def load_model(labelmap, device):
         prompts += [label, "a photo of " + label, "a " + label + " in an environment"]
     print("Initializing priors from labels...")
     inputs = processor(text=[prompts], images=Image.new("RGB", (224, 224)), return_tensors="pt")
-    with torch.no_grad():
-        queries = hf(**inputs).text_embeds
+    # reference src/models.py:165-169 `queries = _model(**inputs).text_embeds`: the text tower on the device kernels
+    # (owl_vit_object_detection_b200/text.py); [1, 3 * classes, 512], unit-norm rows
+    queries = text_query_bank(hf, inputs["input_ids"], inputs.get("attention_mask"), device)
     model = OwlViT(pretrained_model=hf, query_bank=queries)
     keep = set(trainable_names(model.cfg))
     print("Trainable parameters:")

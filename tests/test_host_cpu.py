@@ -26,7 +26,7 @@ def test_cabi_exports_every_declared_symbol():
     assert len(names) >= 20, names
     for n in names:
         assert hasattr(lib, n), f"libowl_b200.so does not export {n}"
-    assert lib.owl_abi_version() == 5
+    assert lib.owl_abi_version() == 6
     # argument validation works without a GPU and reports through owl_last_error
     assert lib.owl_gemm(None, None) != 0
     assert b"null" in lib.owl_last_error()
