@@ -147,6 +147,19 @@ int owl_attn_bwd(const void* qkv_f16, const void* dctx_f16, const float* lse, co
 long long owl_preprocess_workspace_bytes(int H, int W, int out_size);
 int owl_preprocess_image(const uint8_t* img_hwc, int H, int W, long long row_stride_bytes, const float* lut,
                          float* out_chw, int out_size, void* workspace, long long workspace_bytes, void* stream);
+/* The same for a batch of n images of DIFFERENT sizes in three launches per 32 images (coefficients, horizontal pass,
+ * vertical pass) instead of per image: images_host is a HOST array of descriptors (device pixel pointer, height,
+ * width, bytes between rows), out_nchw [n][3][out_size][out_size] f32.  What a collate function for batch > 1 needs
+ * (reference src/dataset.py:101-106 is batch-1).  workspace: owl_preprocess_batch_workspace_bytes(...) bytes. */
+#define OWL_PRE_MAX_BATCH 32
+typedef struct owl_pre_image {
+  const uint8_t* pixels;
+  int H, W;
+  long long row_stride_bytes;
+} owl_pre_image;
+long long owl_preprocess_batch_workspace_bytes(const owl_pre_image* images_host, int n, int out_size);
+int owl_preprocess_batch(const owl_pre_image* images_host, int n, const float* lut, float* out_nchw, int out_size,
+                         void* workspace, long long workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Detection post-processing (reference src/models.py:122-146 `PostProcess`, eval path main.py:110-118): per image,

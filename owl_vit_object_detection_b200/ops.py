@@ -273,8 +273,43 @@ def preprocess_image(img_hwc: torch.Tensor, lut: torch.Tensor, out_chw: torch.Te
     H, W = int(img_hwc.shape[0]), int(img_hwc.shape[1])
     check(lib().owl_preprocess_image(_vp(img_hwc), H, W, ctypes.c_longlong(img_hwc.stride(0)), _vp(lut), _vp(out_chw),
                                      int(out_chw.shape[1]), _vp(workspace), ctypes.c_longlong(workspace.numel()), _sp()),
-          "owl_preprocess_image", kernels=4)
+          "owl_preprocess_image", kernels=3)
     return out_chw
+
+
+class PreImage(ctypes.Structure):
+    """Mirror of `struct owl_pre_image` (include/owl_b200.h)."""
+    _fields_ = [("pixels", ctypes.c_void_p), ("H", ctypes.c_int), ("W", ctypes.c_int),
+                ("row_stride_bytes", ctypes.c_longlong)]
+
+
+def _pre_descriptors(images):
+    arr = (PreImage * len(images))()
+    for i, im in enumerate(images):
+        assert im.is_cuda and im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == 3, (im.dtype, im.shape)
+        assert im.stride(2) == 1 and im.stride(1) == 3, "pixels must be packed RGB"
+        arr[i].pixels, arr[i].H, arr[i].W = im.data_ptr(), int(im.shape[0]), int(im.shape[1])
+        arr[i].row_stride_bytes = int(im.stride(0))
+    return arr
+
+
+def preprocess_batch_workspace_bytes(images, out_size: int) -> int:
+    fn = lib().owl_preprocess_batch_workspace_bytes
+    fn.restype = ctypes.c_longlong
+    return int(fn(_pre_descriptors(images), len(images), out_size))
+
+
+def preprocess_batch(images, lut: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor) -> torch.Tensor:
+    """uint8 [H_i, W_i, 3] CUDA images of different sizes -> out [n, 3, S, S] fp32 in three launches per 32 images
+    (owl_preprocess_batch: Pillow-exact bicubic resize + the rescale / normalise lut)."""
+    n = len(images)
+    _f32(lut), _f32(out)
+    assert lut.numel() == 768 and out.dim() == 4 and out.shape[0] == n and out.shape[1] == 3
+    assert out.shape[2] == out.shape[3] and workspace.dtype == torch.uint8 and workspace.is_cuda
+    check(lib().owl_preprocess_batch(_pre_descriptors(images), n, _vp(lut), _vp(out), int(out.shape[2]), _vp(workspace),
+                                     ctypes.c_longlong(workspace.numel()), _sp()),
+          "owl_preprocess_batch", kernels=3 * ((n + 31) // 32))
+    return out
 
 
 def postprocess(boxes: torch.Tensor, sims: torch.Tensor, confidence_threshold: float, iou_threshold: float):

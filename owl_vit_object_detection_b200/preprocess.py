@@ -2,7 +2,8 @@
 image goes through HF `OwlViTProcessor` = bicubic resize to 768 x 768, /255, CLIP mean / std, channels first).
 
 `DevicePreprocessor` takes raw uint8 RGB images (HWC, any size) and produces the model's `[B, 3, S, S]` fp32
-`pixel_values` with `owl_preprocess_image` (Pillow-exact resample, see csrc/preprocess.cu).  The host ships one
+`pixel_values` with `owl_preprocess_batch` (Pillow-exact resample, three launches for a whole batch of images of
+different sizes, see csrc/preprocess.cu).  The host ships one
 byte per channel instead of a 7 MB fp32 tensor per image and no DataLoader worker has to resize anything.
 """
 from __future__ import annotations
@@ -42,12 +43,15 @@ class DevicePreprocessor:
         if out is None:
             out = torch.empty((B, 3, S, S), dtype=torch.float32, device=self.device)
         assert out.shape == (B, 3, S, S) and out.is_contiguous()
-        need = max(ops.preprocess_workspace_bytes(int(im.shape[0]), int(im.shape[1]), S) for im in images)
-        if self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        dev_images = []
         for b, im in enumerate(images):
             if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3:
                 raise ValueError(f"image {b}: expected uint8 [H, W, 3], got {im.dtype} {tuple(im.shape)}")
-            im = im.to(self.device, non_blocking=True).contiguous()
-            ops.preprocess_image(im, self.lut, out[b], self._ws)     # stream-ordered: the workspace is reused
+            dev_images.append(im.to(self.device, non_blocking=True).contiguous())
+        with torch.cuda.device(self.device):
+            need = ops.preprocess_batch_workspace_bytes(dev_images, S)
+            if self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            # the whole ragged batch in three launches per 32 images (stream-ordered: the workspace is reused)
+            ops.preprocess_batch(dev_images, self.lut, out, self._ws)
         return out

@@ -64,3 +64,26 @@ def test_raw_uint8_at_model_resolution_is_one_fused_pass_and_bit_equal():
         b0, _, s0, _ = model(raw)
         b1, _, s1, _ = model(ref32)
     assert torch.equal(b0, b1) and torch.equal(s0, s1)
+
+
+def test_ragged_batch_in_three_launches_equals_per_image():
+    """A batch of images of different sizes through ONE owl_preprocess_batch call (3 launches per 32 images) equals the
+    oracle per image, and the single-image entry point, bit for bit; 40 images exercise the chunking."""
+    from owl_vit_object_detection_b200 import _lib, ops
+    from owl_vit_object_detection_b200.preprocess import DevicePreprocessor
+    size = 96
+    geoms = [(37 + 11 * (i % 7), 29 + 13 * (i % 5)) for i in range(40)] + [(1, 1), (200, 3), (96, 96)]
+    raws = [synth.make_raw_image(h, w, seed=50 + i) for i, (h, w) in enumerate(geoms)]
+    pre_dev = DevicePreprocessor(size)
+    l0 = _lib.KERNEL_LAUNCHES
+    out = pre_dev([torch.from_numpy(r) for r in raws])
+    assert _lib.KERNEL_LAUNCHES - l0 == 3 * 2          # 43 images = two chunks of <= 32
+    out = out.cpu().numpy()
+    for i, r in enumerate(raws):
+        np.testing.assert_array_equal(out[i], pre.preprocess(r, size), err_msg=f"image {i} {geoms[i]}")
+    # single-image C entry point (kept for callers that hold one image)
+    im = torch.from_numpy(raws[3]).cuda()
+    ws = torch.empty(ops.preprocess_workspace_bytes(im.shape[0], im.shape[1], size), dtype=torch.uint8, device="cuda")
+    one = torch.empty((3, size, size), dtype=torch.float32, device="cuda")
+    ops.preprocess_image(im, pre_dev.lut, one, ws)
+    np.testing.assert_array_equal(one.cpu().numpy(), out[3])
