@@ -228,13 +228,18 @@ int owl_rownorm_bwd(const float* e, const float* dy, void* out, int rows, int E,
 int owl_box_tail_bwd(const float* dboxes, const float* sig, const float* w2, const void* pre1_f16,
                      const void* h1_f16, const float* gscale, float* dz, void* dpre1_f16, float* dw2, float* db2,
                      int M, int D, void* stream);
-/* bias gradients: out[n] += (gscale ? gscale[1] : 1) * sum_m x[m, n]   (x fp16 or fp32, N and ld even). */
-int owl_colsum(const void* x, int is_f16, long long ld, int M, int N, const float* gscale, float* out, void* stream);
+/* bias gradients: out[n] += (gscale ? gscale[1] : 1) * sum_m x[m, n]   (x fp16 or fp32, N and ld even).
+ * cast_out_f16 (optional, fp32 input, N and ld multiples of 4): also writes x as fp16 [M, N] in the same pass - the
+ * operand of the next backward GEMMs (one read of the gradient instead of a cast pass plus a column-sum pass). */
+int owl_colsum(const void* x, int is_f16, long long ld, int M, int N, const float* gscale, float* out,
+               void* cast_out_f16, void* stream);
 /* LayerNorm backward (HF:498,507; reference src/models.py:80): dx = dx_add + LN'(dy) (dx may be NULL when only the
- * parameter gradients are needed); dgamma / dbeta += 1/S * sums. */
+ * parameter gradients are needed); dgamma / dbeta += 1/S * sums.  dx_f16 + dx_colsum (optional, together): dx is also -
+ * or, with dx == NULL, only - written as fp16 [rows, D] and its column sums (the bias gradient of the Linear that
+ * produced the LayerNorm's input, HF:459) are added to dx_colsum, so the fp32 dx never travels through HBM. */
 int owl_layernorm_bwd(const float* x, long long x_stride, const float* dy, long long dy_stride, const float* gamma,
                       const float* dx_add, float* dx, long long dx_stride, float* dgamma, float* dbeta, int rows,
-                      int D, float eps, const float* gscale, void* stream);
+                      int D, float eps, const float* gscale, void* dx_f16, float* dx_colsum, void* stream);
 /* backward of owl_post_fuse: dx rows of the patch tokens, dcl [B,D] += (scaled), LayerNorm parameter grads += . */
 int owl_post_fuse_bwd(const float* x, const float* ecls, const float* g1, const float* b1, const float* g2,
                       const float* dfeats, float* dx, float* dcl, float* dg1, float* db1, float* dg2, float* db2,

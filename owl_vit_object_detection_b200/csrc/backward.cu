@@ -231,27 +231,99 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, int M, int 
   }
 }
 
+// Vectorised flavour (N, ld multiples of the 16-byte vector, aligned base): a thread owns VEC = 16 / sizeof(T)
+// consecutive columns and reads 16 bytes per row with four rows in flight; a warp covers 32 * VEC columns of a row
+// (512 bytes), the eight warps of a CTA take interleaved rows of the CTA's row range.  Optionally writes the fp16 copy
+// of an fp32 input in the same pass (the cast the next GEMM's operand needs: one read of the gradient instead of two).
+constexpr int CS_WARPS = 8;
+template <typename T, bool CAST>
+__global__ void __launch_bounds__(CS_WARPS * 32)
+colsum_vec_kernel(const T* __restrict__ x, long long ld, int M, int N, int rows_per_cta,
+                  const float* __restrict__ gscale, float* __restrict__ out, __half* __restrict__ y16, long long ldy) {
+  constexpr int VEC = 16 / sizeof(T);
+  pdl_grid_wait();
+  __shared__ float red[CS_WARPS][32 * VEC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * 32 + lane) * VEC;
+  const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  if (c < N) {
+    for (int m = m0 + warp; m < m1; m += 4 * CS_WARPS) {
+      uint4 v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int mm = min(m + r * CS_WARPS, M - 1);
+        v[r] = *reinterpret_cast<const uint4*>(x + mm * ld + c);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (m + r * CS_WARPS < m1) {
+          if constexpr (sizeof(T) == 2) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[r]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(h[k]);
+              acc[2 * k] += f.x;
+              acc[2 * k + 1] += f.y;
+            }
+          } else {
+            const float* f = reinterpret_cast<const float*>(&v[r]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] += f[k];
+            if constexpr (CAST) {
+              const __half2 lo = __floats2half2_rn(f[0], f[1]), hi = __floats2half2_rn(f[2], f[3]);
+              uint2 o;
+              o.x = *reinterpret_cast<const uint32_t*>(&lo);
+              o.y = *reinterpret_cast<const uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(y16 + (m + r * CS_WARPS) * ldy + c) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) red[warp][lane * VEC + k] = acc[k];
+  __syncthreads();
+  const float us = gscale ? gscale[1] : 1.0f;
+  for (int j = threadIdx.x; j < 32 * VEC; j += CS_WARPS * 32) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < CS_WARPS; ++w) sum += red[w][j];
+    const int cc = blockIdx.x * 32 * VEC + j;
+    if (cc < N) atomicAdd(out + cc, sum * us);
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm backward
 // y = xh * gamma + beta, xh = (x - mean) * rstd.
 //   dx = rstd * (g - mean(g) - xh * mean(g * xh)),  g = dy * gamma          (+ dx_add when given)
 //   dgamma += us * sum_rows dy * xh;  dbeta += us * sum_rows dy
 // CTA = 4 warps, each warp walks rows r0 + w, r0 + w + 4, ... of its chunk and keeps private parameter-gradient
 // accumulators in shared memory; one set of global atomics per CTA.
+// EXTRA: dx is also (or only: dx may be NULL) written as the fp16 operand of the next backward GEMMs (dx16, row stride
+// D) and its column sums - the bias gradient of the Linear whose output dx is the gradient of - are accumulated into
+// dxsum; the fp32 gradient then never travels through HBM (28 MB written + twice read at batch 16 otherwise).
 constexpr int LNB_WARPS = 4;
 
-template <int NV>
+template <int NV, bool EXTRA>
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ dy, long long dy_stride,
               const float* __restrict__ gamma, const float* __restrict__ dx_add, float* __restrict__ dx,
               long long dx_stride, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, float eps,
-              int rows_per_cta, const float* __restrict__ gscale) {
+              int rows_per_cta, const float* __restrict__ gscale, __half* __restrict__ dx16,
+              float* __restrict__ dxsum) {
   constexpr int D = NV * 128;
+  constexpr int NACC = EXTRA ? 3 : 2;
   pdl_grid_wait();
-  extern __shared__ float lnb_sm[];  // [LNB_WARPS][2][D]
+  extern __shared__ float lnb_sm[];  // [LNB_WARPS][NACC][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* accg = lnb_sm + (warp * 2) * D;
+  float* accg = lnb_sm + (warp * NACC) * D;
   float* accb = accg + D;
-  for (int i = lane; i < 2 * D; i += 32) accg[i] = 0.f;
+  float* accs = accb + D;            // EXTRA only
+  for (int i = lane; i < NACC * D; i += 32) accg[i] = 0.f;
   float4 gm[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
@@ -293,7 +365,7 @@ ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
       sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
       sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
     }
-    if (dx) {
+    if (dx || EXTRA) {
       const float mg = bw_warp_sum(sg) / D, mgx = bw_warp_sum(sgx) / D;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -302,18 +374,33 @@ ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
         o.x = rstd * (gv[i].x - mg - xv[i].x * mgx); o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
         o.z = rstd * (gv[i].z - mg - xv[i].z * mgx); o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
         if (dx_add) { o.x += av[i].x; o.y += av[i].y; o.z += av[i].z; o.w += av[i].w; }
-        *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
+        if (dx) *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
+        if constexpr (EXTRA) {
+          float4 sacc = *reinterpret_cast<float4*>(accs + c);
+          sacc.x += o.x; sacc.y += o.y; sacc.z += o.z; sacc.w += o.w;
+          *reinterpret_cast<float4*>(accs + c) = sacc;
+          const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(dx16 + static_cast<long long>(row) * D + c) = pk;
+        }
       }
     }
   }
   __syncthreads();
   const float us = gscale ? gscale[1] : 1.0f;
   for (int i = threadIdx.x; i < D; i += LNB_WARPS * 32) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, sx = 0.f;
 #pragma unroll
-    for (int w = 0; w < LNB_WARPS; ++w) { a += lnb_sm[(w * 2) * D + i]; b += lnb_sm[(w * 2 + 1) * D + i]; }
+    for (int w = 0; w < LNB_WARPS; ++w) {
+      a += lnb_sm[(w * NACC) * D + i];
+      b += lnb_sm[(w * NACC + 1) * D + i];
+      if constexpr (EXTRA) sx += lnb_sm[(w * NACC + 2) * D + i];
+    }
     atomicAdd(dgamma + i, a * us);
     atomicAdd(dbeta + i, b * us);
+    if constexpr (EXTRA) atomicAdd(dxsum + i, sx * us);
   }
 }
 
@@ -541,10 +628,35 @@ extern "C" int owl_box_tail_bwd(const float* dboxes, const float* sig, const flo
 }
 
 extern "C" int owl_colsum(const void* x, int is_f16, long long ld, int M, int N, const float* gscale, float* out,
-                          void* stream) {
+                          void* cast_out_f16, void* stream) {
   OWL_CHECK_ARG(x && out && M > 0 && N > 0 && N % 2 == 0 && ld % 2 == 0, "colsum: bad arguments (N, ld even)");
-  dim3 grid((N + 63) / 64, (M + 255) / 256), block(32, 8);
+  OWL_CHECK_ARG(!cast_out_f16 || !is_f16, "colsum: the fused fp16 copy is for fp32 input");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int vec = is_f16 ? 8 : 4;
+  const bool aligned = N % vec == 0 && ld % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                       (!cast_out_f16 || (reinterpret_cast<uintptr_t>(cast_out_f16) & 7) == 0);
+  if (aligned) {
+    // rows per CTA: about four CTAs per SM in total, a multiple of the 32 rows one pass of the CTA covers
+    const int col_blocks = (N + 32 * vec - 1) / (32 * vec);
+    int row_blocks = (4 * num_sms() + col_blocks - 1) / col_blocks;
+    int rows_per_cta = (M + row_blocks - 1) / row_blocks;
+    rows_per_cta = ((rows_per_cta + 4 * CS_WARPS - 1) / (4 * CS_WARPS)) * (4 * CS_WARPS);
+    row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
+    dim3 grid(col_blocks, row_blocks);
+    if (is_f16)
+      OWL_LAUNCH((colsum_vec_kernel<__half, false>), grid, CS_WARPS * 32, 0, s, static_cast<const __half*>(x), ld, M, N,
+                 rows_per_cta, gscale, out, static_cast<__half*>(nullptr), 0LL);
+    else if (cast_out_f16)
+      OWL_LAUNCH((colsum_vec_kernel<float, true>), grid, CS_WARPS * 32, 0, s, static_cast<const float*>(x), ld, M, N,
+                 rows_per_cta, gscale, out, static_cast<__half*>(cast_out_f16), static_cast<long long>(N));
+    else
+      OWL_LAUNCH((colsum_vec_kernel<float, false>), grid, CS_WARPS * 32, 0, s, static_cast<const float*>(x), ld, M, N,
+                 rows_per_cta, gscale, out, static_cast<__half*>(nullptr), 0LL);
+    OWL_CUDA(cudaGetLastError());
+    return OWL_OK;
+  }
+  OWL_CHECK_ARG(!cast_out_f16, "colsum: the fused fp16 copy needs N and ld to be multiples of 4 and a 16-byte aligned input");
+  dim3 grid((N + 63) / 64, (M + 255) / 256), block(32, 8);
   if (is_f16) OWL_LAUNCH(colsum_kernel<__half>, grid, block, 0, s, static_cast<const __half*>(x), ld, M, N, gscale, out);
   else OWL_LAUNCH(colsum_kernel<float>, grid, block, 0, s, static_cast<const float*>(x), ld, M, N, gscale, out);
   OWL_CUDA(cudaGetLastError());
@@ -554,17 +666,25 @@ extern "C" int owl_colsum(const void* x, int is_f16, long long ld, int M, int N,
 extern "C" int owl_layernorm_bwd(const float* x, long long x_stride, const float* dy, long long dy_stride,
                                  const float* gamma, const float* dx_add, float* dx, long long dx_stride,
                                  float* dgamma, float* dbeta, int rows, int D, float eps, const float* gscale,
-                                 void* stream) {
+                                 void* dx_f16, float* dx_colsum, void* stream) {
   OWL_CHECK_ARG(x && dy && gamma && dgamma && dbeta && rows > 0, "layernorm_bwd: bad arguments");
   OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * BW_MAX_VEC, "layernorm_bwd: unsupported D = %d", D);
-  OWL_CHECK_ARG(!dx_add || dx, "layernorm_bwd: dx_add needs dx");
+  OWL_CHECK_ARG(!dx_add || dx || dx_f16, "layernorm_bwd: dx_add needs dx or dx_f16");
+  OWL_CHECK_ARG((dx_f16 == nullptr) == (dx_colsum == nullptr), "layernorm_bwd: dx_f16 and dx_colsum come together");
   const int rows_per_cta = rows >= 148 * 16 ? 16 : (rows >= 148 * 4 ? 8 : 4);
-  const size_t smem = sizeof(float) * LNB_WARPS * 2 * D;
+  const bool extra = dx_f16 != nullptr;
+  const size_t smem = sizeof(float) * LNB_WARPS * (extra ? 3 : 2) * D;
 #define OWL_LNB_CASE(NV)                                                                                              \
   case NV:                                                                                                            \
-    OWL_LAUNCH(ln_bwd_kernel<NV>, (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem,                     \
-               static_cast<cudaStream_t>(stream), x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma,  \
-               dbeta, rows, eps, rows_per_cta, gscale);                                                               \
+    if (extra)                                                                                                        \
+      OWL_LAUNCH((ln_bwd_kernel<NV, true>), (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem,           \
+                 static_cast<cudaStream_t>(stream), x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma, \
+                 dbeta, rows, eps, rows_per_cta, gscale, static_cast<__half*>(dx_f16), dx_colsum);                    \
+    else                                                                                                              \
+      OWL_LAUNCH((ln_bwd_kernel<NV, false>), (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem,          \
+                 static_cast<cudaStream_t>(stream), x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma, \
+                 dbeta, rows, eps, rows_per_cta, gscale, static_cast<__half*>(nullptr),                               \
+                 static_cast<float*>(nullptr));                                                                       \
     break;
   switch (D / 128) {
     OWL_LNB_CASE(1) OWL_LNB_CASE(2) OWL_LNB_CASE(3) OWL_LNB_CASE(4) OWL_LNB_CASE(5) OWL_LNB_CASE(6) OWL_LNB_CASE(7)

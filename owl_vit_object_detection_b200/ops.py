@@ -363,19 +363,29 @@ def box_tail_bwd(dboxes, sig, w2, pre1_16, h1_16, gscale, dz, dpre1_16, dw2, db2
                                  _vp(dpre1_16), _vp(dw2), _vp(db2), M, D, _sp()), "owl_box_tail_bwd", kernels=2)
 
 
-def colsum(x: torch.Tensor, out: torch.Tensor, *, M: int, N: int, gscale=None, ld: Optional[int] = None):
+def colsum(x: torch.Tensor, out: torch.Tensor, *, M: int, N: int, gscale=None, ld: Optional[int] = None,
+           cast_to: Optional[torch.Tensor] = None):
+    """out[n] += unscale * sum_m x[m, n]; `cast_to` (fp32 x only) also receives x as fp16 [M, N] in the same pass."""
     assert x.dtype in (torch.float16, torch.float32) and out.dtype == torch.float32
+    if cast_to is not None:
+        assert x.dtype == torch.float32 and cast_to.dtype == torch.float16 and cast_to.is_contiguous()
+        assert cast_to.numel() == M * N
     check(lib().owl_colsum(_vp(x), int(x.dtype == torch.float16), _ll(x.stride(-2) if ld is None else ld), M, N,
-                           _vp(gscale), _vp(out), _sp()), "owl_colsum")
+                           _vp(gscale), _vp(out), _vp(cast_to), _sp()), "owl_colsum")
     return out
 
 
 def layernorm_bwd(x, dy, gamma, dgamma, dbeta, *, rows: int, D: int, eps: float, gscale=None, dx=None, dx_add=None,
-                  x_stride: Optional[int] = None, dy_stride: Optional[int] = None, dx_stride: Optional[int] = None):
+                  x_stride: Optional[int] = None, dy_stride: Optional[int] = None, dx_stride: Optional[int] = None,
+                  dx16: Optional[torch.Tensor] = None, dx_colsum: Optional[torch.Tensor] = None):
+    """dx16 / dx_colsum (together): dx additionally (dx=None: only) as fp16 [rows, D] + its column sums += ."""
+    if dx16 is not None:
+        assert dx16.dtype == torch.float16 and dx16.is_contiguous() and dx16.numel() == rows * D
+        assert dx_colsum is not None and dx_colsum.dtype == torch.float32 and dx_colsum.numel() == D
     check(lib().owl_layernorm_bwd(_vp(x), _ll(D if x_stride is None else x_stride), _vp(dy),
                                   _ll(D if dy_stride is None else dy_stride), _vp(gamma), _vp(dx_add), _vp(dx),
                                   _ll(D if dx_stride is None else dx_stride), _vp(dgamma), _vp(dbeta), rows, D,
-                                  _fl(eps), _vp(gscale), _sp()), "owl_layernorm_bwd")
+                                  _fl(eps), _vp(gscale), _vp(dx16), _vp(dx_colsum), _sp()), "owl_layernorm_bwd")
 
 
 def post_fuse_bwd(x, ecls, g1, b1, g2, dfeats, dx, dcl, dg1, db1, dg2, db2, *, B: int, P: int, D: int, eps: float,
