@@ -234,12 +234,10 @@ int owl_box_tail_bwd(const float* dboxes, const float* sig, const float* w2, con
 int owl_colsum(const void* x, int is_f16, long long ld, int M, int N, const float* gscale, float* out,
                void* cast_out_f16, void* stream);
 /* LayerNorm backward (HF:498,507; reference src/models.py:80): dx = dx_add + LN'(dy) (dx may be NULL when only the
- * parameter gradients are needed); dgamma / dbeta += 1/S * sums.  dx_f16 + dx_colsum (optional, together): dx is also -
- * or, with dx == NULL, only - written as fp16 [rows, D] and its column sums (the bias gradient of the Linear that
- * produced the LayerNorm's input, HF:459) are added to dx_colsum, so the fp32 dx never travels through HBM. */
+ * parameter gradients are needed); dgamma / dbeta += 1/S * sums. */
 int owl_layernorm_bwd(const float* x, long long x_stride, const float* dy, long long dy_stride, const float* gamma,
                       const float* dx_add, float* dx, long long dx_stride, float* dgamma, float* dbeta, int rows,
-                      int D, float eps, const float* gscale, void* dx_f16, float* dx_colsum, void* stream);
+                      int D, float eps, const float* gscale, void* stream);
 /* backward of owl_post_fuse: dx rows of the patch tokens, dcl [B,D] += (scaled), LayerNorm parameter grads += . */
 int owl_post_fuse_bwd(const float* x, const float* ecls, const float* g1, const float* b1, const float* g2,
                       const float* dfeats, float* dx, float* dcl, float* dg1, float* db1, float* dg2, float* db2,

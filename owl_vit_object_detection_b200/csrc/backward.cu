@@ -303,27 +303,21 @@ colsum_vec_kernel(const T* __restrict__ x, long long ld, int M, int N, int rows_
 //   dgamma += us * sum_rows dy * xh;  dbeta += us * sum_rows dy
 // CTA = 4 warps, each warp walks rows r0 + w, r0 + w + 4, ... of its chunk and keeps private parameter-gradient
 // accumulators in shared memory; one set of global atomics per CTA.
-// EXTRA: dx is also (or only: dx may be NULL) written as the fp16 operand of the next backward GEMMs (dx16, row stride
-// D) and its column sums - the bias gradient of the Linear whose output dx is the gradient of - are accumulated into
-// dxsum; the fp32 gradient then never travels through HBM (28 MB written + twice read at batch 16 otherwise).
 constexpr int LNB_WARPS = 4;
 
-template <int NV, bool EXTRA>
+template <int NV>
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __restrict__ dy, long long dy_stride,
               const float* __restrict__ gamma, const float* __restrict__ dx_add, float* __restrict__ dx,
               long long dx_stride, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, float eps,
-              int rows_per_cta, const float* __restrict__ gscale, __half* __restrict__ dx16,
-              float* __restrict__ dxsum) {
+              int rows_per_cta, const float* __restrict__ gscale) {
   constexpr int D = NV * 128;
-  constexpr int NACC = EXTRA ? 3 : 2;
   pdl_grid_wait();
-  extern __shared__ float lnb_sm[];  // [LNB_WARPS][NACC][D]
+  extern __shared__ float lnb_sm[];  // [LNB_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* accg = lnb_sm + (warp * NACC) * D;
+  float* accg = lnb_sm + (warp * 2) * D;
   float* accb = accg + D;
-  float* accs = accb + D;            // EXTRA only
-  for (int i = lane; i < NACC * D; i += 32) accg[i] = 0.f;
+  for (int i = lane; i < 2 * D; i += 32) accg[i] = 0.f;
   float4 gm[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
@@ -365,7 +359,7 @@ ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
       sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
       sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
     }
-    if (dx || EXTRA) {
+    if (dx) {
       const float mg = bw_warp_sum(sg) / D, mgx = bw_warp_sum(sgx) / D;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -374,33 +368,18 @@ ln_bwd_kernel(const float* __restrict__ x, long long x_stride, const float* __re
         o.x = rstd * (gv[i].x - mg - xv[i].x * mgx); o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
         o.z = rstd * (gv[i].z - mg - xv[i].z * mgx); o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
         if (dx_add) { o.x += av[i].x; o.y += av[i].y; o.z += av[i].z; o.w += av[i].w; }
-        if (dx) *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
-        if constexpr (EXTRA) {
-          float4 sacc = *reinterpret_cast<float4*>(accs + c);
-          sacc.x += o.x; sacc.y += o.y; sacc.z += o.z; sacc.w += o.w;
-          *reinterpret_cast<float4*>(accs + c) = sacc;
-          const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(dx16 + static_cast<long long>(row) * D + c) = pk;
-        }
+        *reinterpret_cast<float4*>(dx + row * dx_stride + c) = o;
       }
     }
   }
   __syncthreads();
   const float us = gscale ? gscale[1] : 1.0f;
   for (int i = threadIdx.x; i < D; i += LNB_WARPS * 32) {
-    float a = 0.f, b = 0.f, sx = 0.f;
+    float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int w = 0; w < LNB_WARPS; ++w) {
-      a += lnb_sm[(w * NACC) * D + i];
-      b += lnb_sm[(w * NACC + 1) * D + i];
-      if constexpr (EXTRA) sx += lnb_sm[(w * NACC + 2) * D + i];
-    }
+    for (int w = 0; w < LNB_WARPS; ++w) { a += lnb_sm[(w * 2) * D + i]; b += lnb_sm[(w * 2 + 1) * D + i]; }
     atomicAdd(dgamma + i, a * us);
     atomicAdd(dbeta + i, b * us);
-    if constexpr (EXTRA) atomicAdd(dxsum + i, sx * us);
   }
 }
 
@@ -641,6 +620,9 @@ extern "C" int owl_colsum(const void* x, int is_f16, long long ld, int M, int N,
     int row_blocks = (4 * num_sms() + col_blocks - 1) / col_blocks;
     int rows_per_cta = (M + row_blocks - 1) / row_blocks;
     rows_per_cta = ((rows_per_cta + 4 * CS_WARPS - 1) / (4 * CS_WARPS)) * (4 * CS_WARPS);
+    // up to 256 rows: ONE row block, i.e. one atomic per column and a run-to-run deterministic sum (a bias gradient
+    // that is mathematically zero - k_proj.bias - is pure rounding noise whose sign decides a +-lr Adam step)
+    if (M <= 256) rows_per_cta = 256;
     row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
     dim3 grid(col_blocks, row_blocks);
     if (is_f16)
@@ -666,25 +648,17 @@ extern "C" int owl_colsum(const void* x, int is_f16, long long ld, int M, int N,
 extern "C" int owl_layernorm_bwd(const float* x, long long x_stride, const float* dy, long long dy_stride,
                                  const float* gamma, const float* dx_add, float* dx, long long dx_stride,
                                  float* dgamma, float* dbeta, int rows, int D, float eps, const float* gscale,
-                                 void* dx_f16, float* dx_colsum, void* stream) {
+                                 void* stream) {
   OWL_CHECK_ARG(x && dy && gamma && dgamma && dbeta && rows > 0, "layernorm_bwd: bad arguments");
   OWL_CHECK_ARG(D % 128 == 0 && D <= 128 * BW_MAX_VEC, "layernorm_bwd: unsupported D = %d", D);
-  OWL_CHECK_ARG(!dx_add || dx || dx_f16, "layernorm_bwd: dx_add needs dx or dx_f16");
-  OWL_CHECK_ARG((dx_f16 == nullptr) == (dx_colsum == nullptr), "layernorm_bwd: dx_f16 and dx_colsum come together");
+  OWL_CHECK_ARG(!dx_add || dx, "layernorm_bwd: dx_add needs dx");
   const int rows_per_cta = rows >= 148 * 16 ? 16 : (rows >= 148 * 4 ? 8 : 4);
-  const bool extra = dx_f16 != nullptr;
-  const size_t smem = sizeof(float) * LNB_WARPS * (extra ? 3 : 2) * D;
+  const size_t smem = sizeof(float) * LNB_WARPS * 2 * D;
 #define OWL_LNB_CASE(NV)                                                                                              \
   case NV:                                                                                                            \
-    if (extra)                                                                                                        \
-      OWL_LAUNCH((ln_bwd_kernel<NV, true>), (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem,           \
-                 static_cast<cudaStream_t>(stream), x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma, \
-                 dbeta, rows, eps, rows_per_cta, gscale, static_cast<__half*>(dx_f16), dx_colsum);                    \
-    else                                                                                                              \
-      OWL_LAUNCH((ln_bwd_kernel<NV, false>), (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem,          \
-                 static_cast<cudaStream_t>(stream), x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma, \
-                 dbeta, rows, eps, rows_per_cta, gscale, static_cast<__half*>(nullptr),                               \
-                 static_cast<float*>(nullptr));                                                                       \
+    OWL_LAUNCH(ln_bwd_kernel<NV>, (rows + rows_per_cta - 1) / rows_per_cta, LNB_WARPS * 32, smem,                     \
+               static_cast<cudaStream_t>(stream), x, x_stride, dy, dy_stride, gamma, dx_add, dx, dx_stride, dgamma,  \
+               dbeta, rows, eps, rows_per_cta, gscale);                                                               \
     break;
   switch (D / 128) {
     OWL_LNB_CASE(1) OWL_LNB_CASE(2) OWL_LNB_CASE(3) OWL_LNB_CASE(4) OWL_LNB_CASE(5) OWL_LNB_CASE(6) OWL_LNB_CASE(7)

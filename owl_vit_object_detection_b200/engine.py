@@ -110,6 +110,7 @@ class Workspace:
             b.dpre0 = z((B * P, D), f16)
             b.dfeats = z((B * P, D), f32)
             b.dx_out = z((B * S, D), f32)
+            b.dx_mid = z((B * S, D), f32)
             b.dcl = z((B, D), f32)
             b.g16 = z((B * S, D), f16)
             b.dmpre = z((B * S, F), f16)
@@ -385,16 +386,16 @@ class Engine:
         self._wgrad(bw.dmpre, ws.h2, gview(p + "mlp.fc1.weight"), rows=M, n_out=F, n_in=D, gscale=gs)
         ops.colsum(bw.dmpre, gview(p + "mlp.fc1.bias"), M=M, N=F, gscale=gs)
         ops.gemm(bw.dmpre, self.p16(p + "mlp.fc1.weight"), bw.dh32, M=M, N=D, K=F, b_mn=True)
-        # d(x_mid) = dx_out + LN2'(dh): only ever read as the fp16 operand of the out-proj backward GEMMs and for the
-        # out-proj bias gradient, so the LayerNorm backward emits exactly those two (no fp32 d(x_mid) in HBM)
         ops.layernorm_bwd(ws.x_mid, bw.dh32, self.p32(p + "layer_norm2.weight"), gview(p + "layer_norm2.weight"),
-                          gview(p + "layer_norm2.bias"), rows=M, D=D, eps=eps, gscale=gs, dx_add=bw.dx_out,
-                          dx16=bw.g16, dx_colsum=gview(p + "self_attn.out_proj.bias"))
+                          gview(p + "layer_norm2.bias"), rows=M, D=D, eps=eps, gscale=gs, dx=bw.dx_mid,
+                          dx_add=bw.dx_out)
 
         if on_ready is not None:
             on_ready(1)
 
         # ---- attention half
+        # out-proj bias gradient + the fp16 operand of the two out-proj backward GEMMs in ONE pass over dx_mid
+        ops.colsum(bw.dx_mid, gview(p + "self_attn.out_proj.bias"), M=M, N=D, gscale=gs, cast_to=bw.g16)
         self._wgrad(bw.g16, ws.ctx, gview(p + "self_attn.out_proj.weight"), rows=M, n_out=D, n_in=D, gscale=gs)
         ops.gemm(bw.g16, self.p16(p + "self_attn.out_proj.weight"), bw.dctx, M=M, N=D, K=D, b_mn=True)
         qkv, dqkv = ws.qkv, bw.dqkv

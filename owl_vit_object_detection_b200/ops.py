@@ -376,16 +376,11 @@ def colsum(x: torch.Tensor, out: torch.Tensor, *, M: int, N: int, gscale=None, l
 
 
 def layernorm_bwd(x, dy, gamma, dgamma, dbeta, *, rows: int, D: int, eps: float, gscale=None, dx=None, dx_add=None,
-                  x_stride: Optional[int] = None, dy_stride: Optional[int] = None, dx_stride: Optional[int] = None,
-                  dx16: Optional[torch.Tensor] = None, dx_colsum: Optional[torch.Tensor] = None):
-    """dx16 / dx_colsum (together): dx additionally (dx=None: only) as fp16 [rows, D] + its column sums += ."""
-    if dx16 is not None:
-        assert dx16.dtype == torch.float16 and dx16.is_contiguous() and dx16.numel() == rows * D
-        assert dx_colsum is not None and dx_colsum.dtype == torch.float32 and dx_colsum.numel() == D
+                  x_stride: Optional[int] = None, dy_stride: Optional[int] = None, dx_stride: Optional[int] = None):
     check(lib().owl_layernorm_bwd(_vp(x), _ll(D if x_stride is None else x_stride), _vp(dy),
                                   _ll(D if dy_stride is None else dy_stride), _vp(gamma), _vp(dx_add), _vp(dx),
                                   _ll(D if dx_stride is None else dx_stride), _vp(dgamma), _vp(dbeta), rows, D,
-                                  _fl(eps), _vp(gscale), _vp(dx16), _vp(dx_colsum), _sp()), "owl_layernorm_bwd")
+                                  _fl(eps), _vp(gscale), _sp()), "owl_layernorm_bwd")
 
 
 def post_fuse_bwd(x, ecls, g1, b1, g2, dfeats, dx, dcl, dg1, db1, dg2, db2, *, B: int, P: int, D: int, eps: float,
