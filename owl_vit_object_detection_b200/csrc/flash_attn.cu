@@ -85,7 +85,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 // Packed fp32 pairs (sm_100: FFMA2 / FADD2 take one issue slot for two lanes of work).  The softmax threads are
 // bound by the number of instructions they issue (four softmax warps share a scheduler with the MMA warp; every
-// instruction added to the loop costs time, every one removed gains it - see the OWL_FA_POLY record in DESIGN.md).
+// instruction added to the loop costs time, every one removed gains it - see the polynomial-exp2 record in DESIGN.md).
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -104,25 +104,6 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// 2^x on the FMA / ALU pipes (no MUFU): x = j + f with j = round(x) taken from the low mantissa bits of x + 1.5 * 2^23
-// and f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (relative error 7.5e-5, below the 4.9e-4 of the fp16
-// rounding the probabilities get anyway); j is added into the exponent field.  The softmax phase of the kernel is
-// MUFU-bound (16 exp2 / clk / SM against 128 FMA lanes), so a fraction of the exponentials leaves through here.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.0f);                       // -inf (masked key) / underflow -> 2^-126, which rounds to 0 in fp16
-  const float xr = x + 12582912.0f;
-  const float f = x - (xr - 12582912.0f);
-  float p = fmaf(0.0551716685f, f, 0.2426111251f);
-  p = fmaf(p, f, 0.6932609677f);
-  p = fmaf(p, f, 0.9999280572f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(xr) << 23));
-}
-// element e of a row's sub-block goes through the polynomial when POLY of every 8 do (spread evenly)
-template <int POLY>
-__device__ __forceinline__ float softmax_exp2(float x, int e) {
-  return (((e & 7) * POLY) & 7) < POLY ? poly_exp2(x) : fast_exp2(x);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Second generation of the forward kernel (the one the engine runs; the first generation above stays selectable
 // with OWL_FA_GEN=1 for A/B timing).  Same row ownership (one softmax thread per query row, 128 TMEM columns per
@@ -158,32 +139,25 @@ __device__ __forceinline__ float softmax_exp2(float x, int e) {
 // Template: KV_ROWS = keys per K/V ring slot (32 or 64), STAGES = ring slots, CTAS = CTAs per SM, SPLIT = separate
 // TMA-producer warp (192 threads) instead of one control warp doing both (160 threads), PROF = clock64
 // instrumentation (dev), UNROLL = the unrolled MMA-warp flavour.
-#ifndef OWL_FA_PACK2_DEFAULT
-#define OWL_FA_PACK2_DEFAULT 1
-#endif
-#ifndef OWL_FA_POLY_DEFAULT
-#define OWL_FA_POLY_DEFAULT 0
-#endif
 constexpr int FA2_SUB = 32;                          // keys per sub-block
 int make_qkv_map(CUtensorMap* out, const void* qkv, int B, int S, int D, uint32_t box_rows);
 
 // ROLES > 0: the control warps follow the four softmax warps and WHICH of them issues the MMAs rotates from CTA to CTA
 // on the same SM (a per-SM counter), so that the MMA warps of the four co-resident CTAs do not all share sub-partition
-// 0 with a softmax warp each: ROLES = 2 -> six warps, MMA warp = warp 4 or 5 (sub-partition 0 or 1); ROLES = 4 ->
-// eight warps (64 registers), MMA warp = warp 4..7 (one per sub-partition), two of the extra warps just exit.
+// 0 with a softmax warp each: ROLES = 2 -> six warps, MMA warp = warp 4 or 5 (sub-partition 0 or 1).  (Eight warps with
+// the MMA warp on any of the four sub-partitions need 64 registers per thread and were slower: 39.0 us at S = 577.)
 __device__ unsigned int g_fa_role[1024];
 
 template <int KV_ROWS, int STAGES, bool SPLIT, int ROLES = 0>
 struct Fa2Cfg {
-  static constexpr int kCtrlWarps = ROLES == 4 ? 4 : (SPLIT ? 2 : 1);
+  static constexpr int kCtrlWarps = SPLIT ? 2 : 1;
   static constexpr int kThreads = (kCtrlWarps + 4) * 32;
   static constexpr int kKvBytes = KV_ROWS * FA_DH * 2;
   static constexpr int kSmem = FA_Q_BYTES + 2 * STAGES * kKvBytes + 1024 + 256;
   static constexpr int kSubsPerSlot = KV_ROWS / FA2_SUB;
 };
 
-template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF, bool UNROLL, bool CTRL_LAST, int POLY,
-          bool PACK2, int ROLES>
+template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF, bool UNROLL, bool CTRL_LAST, bool PACK2, int ROLES>
 __global__ void __launch_bounds__((Fa2Cfg<KV_ROWS, STAGES, SPLIT, ROLES>::kThreads), CTAS)
 flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        __half* __restrict__ ctx, float* __restrict__ lse, int S, int D, int H, float scale_log2,
@@ -200,7 +174,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   };
   using Cfg = Fa2Cfg<KV_ROWS, STAGES, SPLIT, ROLES>;
   constexpr int KV_BYTES = Cfg::kKvBytes, SPS = Cfg::kSubsPerSlot, NCTRL = Cfg::kCtrlWarps;
-  static_assert(ROLES == 0 || (SPLIT && CTRL_LAST), "rotating roles need the producer warp and the control warps last");
+  static_assert(ROLES == 0 || (ROLES == 2 && SPLIT && CTRL_LAST), "rotating roles: producer warp + control warps last");
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -518,8 +492,8 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float p0 = softmax_exp2<POLY>(fmaf(__uint_as_float(r[g * 16 + 2 * i]), scale_log2, -mc), 2 * i);
-          const float p1 = softmax_exp2<POLY>(fmaf(__uint_as_float(r[g * 16 + 2 * i + 1]), scale_log2, -mc), 2 * i + 1);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[g * 16 + 2 * i]), scale_log2, -mc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[g * 16 + 2 * i + 1]), scale_log2, -mc));
           sum0 += p0;
           sum1 += p1;
           const __half2 hp = __floats2half2_rn(p0, p1);
@@ -602,7 +576,7 @@ flash_attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 }
 
 template <int KV_ROWS, int STAGES, int CTAS, bool SPLIT, bool PROF = false, bool UNROLL = false, bool CTRL_LAST = false,
-          int POLY = 0, bool PACK2 = false, int ROLES = 0>
+          bool PACK2 = false, int ROLES = 0>
 static int launch_fa2(const void* qkv_f16, void* ctx_f16, float* lse, int B, int S, int H, float sl2, cudaStream_t stream,
                       long long* prof = nullptr) {
   using Cfg = Fa2Cfg<KV_ROWS, STAGES, SPLIT, ROLES>;
@@ -612,7 +586,7 @@ static int launch_fa2(const void* qkv_f16, void* ctx_f16, float* lse, int B, int
   if (rc) return rc;
   rc = make_qkv_map(&tmKV, qkv_f16, B, S, D, KV_ROWS);
   if (rc) return rc;
-  auto kern = flash_attn_fwd2_kernel<KV_ROWS, STAGES, CTAS, SPLIT, PROF, UNROLL, CTRL_LAST, POLY, PACK2, ROLES>;
+  auto kern = flash_attn_fwd2_kernel<KV_ROWS, STAGES, CTAS, SPLIT, PROF, UNROLL, CTRL_LAST, PACK2, ROLES>;
   static SmemOptIn optin;   // per instantiation
   OWL_CUDA(ensure_smem(optin, kern, Cfg::kSmem));
   const unsigned n_cta = static_cast<unsigned>((S + FA_BM - 1) / FA_BM) * H * B;
@@ -672,11 +646,15 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse
   OWL_CHECK_ARG(head_dim == FA_DH, "flash_attn_fwd: head_dim %d is not built (only 64)", head_dim);
   const int D = H * head_dim;
   const float sl2 = scale * 1.4426950408889634f;
-  // Flavour: 0 (default) picks by sequence length; OWL_FA_GEN = 24 / 26 force a flavour (A/B timing), 34 / 36 the same
-  // with the control warp(s) placed AFTER the softmax warps (highest warp ids), 94 / 95 the instrumented builds of
-  // 24 / 26 (tools/fa_prof.py).
-  //   24 = rolled MMA loop, one control warp, shared K/V barrier: best at S = 577
-  //   26 = unrolled MMA loop, producer warp, separate K / V barriers: best on long sequences (S = 3601)
+  // Flavour: 0 (default) picks by sequence length.  OWL_FA_GEN (dev, A/B timing) forces one:
+  //   24 = rolled MMA loop, one control warp, shared K/V barrier (the default for S <= 1024: 35.2 us at S = 577)
+  //   26 = unrolled MMA loop, producer warp, separate K / V barriers
+  //   41 = 26 with the control warps last and the MMA warp alternating between sub-partitions 0 and 1 from CTA to CTA
+  //        (the default for S > 1024: 288.5 us at S = 3601, B = 4, H = 16; 26: 289.9); 40 = the rolled form of it
+  //   34 / 36 = 24 / 26 with the control warp(s) after the softmax warps and the scalar softmax arithmetic (round-2 A/B)
+  //   94 / 95 = instrumented builds of 24 / 26 (tools/fa_prof.py)
+  // Measured slower and removed again (profiles/r02_fa_poly_sweep.txt, r02_fa_roles_sweep.txt): a fraction of the
+  // exponentials as an FMA-pipe polynomial (40.0 - 44.5 us), eight warps with the MMA warp on any sub-partition (39.0 us).
   static const int generation = [] {
     const char* e = getenv("OWL_FA_GEN");
     return e ? atoi(e) : 0;
@@ -686,49 +664,13 @@ extern "C" int owl_flash_attn_fwd(const void* qkv_f16, void* ctx_f16, float* lse
     return launch_fa2<64, 2, 4, true, true, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st, g_fa_dbg);
   if (generation == 94 && g_fa_dbg != nullptr)
     return launch_fa2<64, 2, 4, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st, g_fa_dbg);
-  const bool long_seq = generation == 26 || generation == 36 || (generation == 0 && S > 1024);
-  const bool ctrl_last = generation == 34 || generation == 36;
-  // OWL_FA_POLY = how many of every 8 exponentials of the softmax run as a polynomial on the FMA pipe instead of the
-  // MUFU (0, 2, 3 or 4; see poly_exp2).  The default is the measured best ("Fused attention").
-  static const int poly = [] {
-    const char* e = getenv("OWL_FA_POLY");
-    return e ? atoi(e) : OWL_FA_POLY_DEFAULT;
-  }();
-  // 40 / 41: rotating MMA warp over sub-partitions 0 / 1 (six warps), rolled / unrolled; 42 / 43: over all four
-  // sub-partitions (eight warps, 64 registers); all with the packed softmax arithmetic
-  if (generation == 40) return launch_fa2<64, 2, 4, true, false, false, true, 0, true, 2>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-  if (generation == 41) return launch_fa2<64, 2, 4, true, false, true, true, 0, true, 2>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-  if (generation == 42) return launch_fa2<64, 2, 4, true, false, false, true, 0, true, 4>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-  if (generation == 43) return launch_fa2<64, 2, 4, true, false, true, true, 0, true, 4>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-  // OWL_FA_PACK2 = 1: the softmax arithmetic on packed fp32 pairs (FFMA2 / FADD2)
-  static const int pack2_on = [] {
-    const char* e = getenv("OWL_FA_PACK2");
-    return e ? atoi(e) : OWL_FA_PACK2_DEFAULT;
-  }();
-  if (pack2_on && !ctrl_last && poly == 0) {
-    // default path.  Long sequences: unrolled flavour with the MMA warp alternating between sub-partitions 0 and 1
-    // (measured 288.5 vs 293.5 us at S = 3601); S = 577: rolled flavour (35.2 us; the rotating flavours 34.8 / 35.3)
-    if (long_seq && generation == 0)
-      return launch_fa2<64, 2, 4, true, false, true, true, 0, true, 2>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    if (long_seq) return launch_fa2<64, 2, 4, true, false, true, false, 0, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    return launch_fa2<64, 2, 4, false, false, false, false, 0, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-  }
-  if (long_seq) {
-    if (ctrl_last) return launch_fa2<64, 2, 4, true, false, true, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    switch (poly) {
-      case 2: return launch_fa2<64, 2, 4, true, false, true, false, 2>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      case 3: return launch_fa2<64, 2, 4, true, false, true, false, 3>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      case 4: return launch_fa2<64, 2, 4, true, false, true, false, 4>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-      default: return launch_fa2<64, 2, 4, true, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    }
-  }
-  if (ctrl_last) return launch_fa2<64, 2, 4, false, false, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-  switch (poly) {
-    case 2: return launch_fa2<64, 2, 4, false, false, false, false, 2>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    case 3: return launch_fa2<64, 2, 4, false, false, false, false, 3>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    case 4: return launch_fa2<64, 2, 4, false, false, false, false, 4>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-    default: return launch_fa2<64, 2, 4, false>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
-  }
+  if (generation == 34) return launch_fa2<64, 2, 4, false, false, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+  if (generation == 36) return launch_fa2<64, 2, 4, true, false, true, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+  if (generation == 40) return launch_fa2<64, 2, 4, true, false, false, true, true, 2>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+  if (generation == 26) return launch_fa2<64, 2, 4, true, false, true, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+  if (generation == 41 || (generation == 0 && S > 1024))
+    return launch_fa2<64, 2, 4, true, false, true, true, true, 2>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
+  return launch_fa2<64, 2, 4, false, false, false, false, true>(qkv_f16, ctx_f16, lse, B, S, H, sl2, st);
 }
 
 extern "C" int owl_attn_delta(const void* ctx_f16, const void* dctx_f16, float* delta, int B, int S, int H, int head_dim,
