@@ -33,3 +33,26 @@ def test_identity_axis_and_constant_image():
     img = synth.make_raw_image(96, 40, seed=3)
     r = pre.resize_bicubic_u8(img, 96, 40)
     np.testing.assert_array_equal(r, img)                             # scale 1 on both axes is the identity
+
+
+def test_oracle_matches_installed_huggingface_processor():
+    """The class the reference calls at src/dataset.py:64-71 (`OwlViTProcessor` -> the OWL-ViT image processor).  The
+    reference pins transformers 4.30.2, whose processor is PIL-based; the installed 5.5.0 keeps that implementation as
+    `OwlViTImageProcessorPil` (constructed from its defaults: no download) and the oracle - hence the device kernels,
+    which tests/test_preprocess_gpu.py holds bit-equal to the oracle - reproduces it BIT FOR BIT.  The torchvision-
+    backed `OwlViTImageProcessor` of 5.5.0 is a different resampler: it differs by one uint8 level after a resize."""
+    from PIL import Image
+    transformers = pytest.importorskip("transformers")
+    if not hasattr(transformers, "OwlViTImageProcessorPil"):
+        pytest.skip("this transformers version has no PIL-backed OWL-ViT image processor")
+    proc = transformers.OwlViTImageProcessorPil()
+    assert proc.size["height"] == 768 and proc.size["width"] == 768
+    for k, (h, w) in enumerate([(480, 640), (333, 500), (768, 768), (90, 120), (1, 1)]):
+        raw = synth.make_raw_image(h, w, seed=20 + k)
+        hf = proc(images=Image.fromarray(raw), return_tensors="np")["pixel_values"][0]
+        np.testing.assert_array_equal(hf, pre.preprocess(raw, 768), err_msg=f"{h} x {w}")
+    fast = transformers.OwlViTImageProcessor()
+    raw = synth.make_raw_image(480, 640, seed=20)
+    hf = fast(images=Image.fromarray(raw), return_tensors="pt")["pixel_values"][0].numpy()
+    one_level = 1.0 / 255.0 / 0.26130258
+    assert np.abs(hf - pre.preprocess(raw, 768)).max() <= 2.1 * one_level
