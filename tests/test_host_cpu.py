@@ -32,6 +32,35 @@ def test_cabi_exports_every_declared_symbol():
     assert b"null" in lib.owl_last_error()
 
 
+def test_header_is_plain_c_and_new_entry_points_validate_without_a_gpu():
+    """include/owl_b200.h must be consumable from C (the FFI of a reference maintainer: cgo / ctypes / cffi), and the
+    entry points added in round 2 reject bad arguments before touching a device (so this runs without a GPU)."""
+    import ctypes
+    from owl_vit_object_detection_b200 import _lib, ops
+    hdr = os.path.join(ROOT, "include", "owl_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    lib = _lib.lib()
+    one = ctypes.c_void_p(16)          # a non-null dummy: validation fails before it is dereferenced
+    assert lib.owl_text_attn(one, None, one, 2, 33, 8, 64, ctypes.c_float(0.125), None) != 0
+    assert b"33 tokens" in lib.owl_last_error()
+    assert lib.owl_text_attn(one, None, one, 2, 16, 8, 32, ctypes.c_float(0.125), None) != 0
+    assert b"head_dim" in lib.owl_last_error()
+    assert lib.owl_text_embed(one, one, one, one, 4, 16, 510, 49408, None, None) != 0
+    assert b"multiple of 4" in lib.owl_last_error()
+    assert lib.owl_colsum(one, 1, ctypes.c_longlong(8), 4, 8, None, one, one, None) != 0
+    assert b"fp32 input" in lib.owl_last_error()
+    # host-only helper: workspace of a ragged batch = sum over the images; an empty side is refused
+    imgs = (ops.PreImage * 2)()
+    imgs[0].pixels, imgs[0].H, imgs[0].W, imgs[0].row_stride_bytes = 16, 480, 640, 1920
+    imgs[1].pixels, imgs[1].H, imgs[1].W, imgs[1].row_stride_bytes = 16, 90, 120, 360
+    fn, one_img = lib.owl_preprocess_batch_workspace_bytes, lib.owl_preprocess_workspace_bytes
+    fn.restype = one_img.restype = ctypes.c_longlong
+    assert fn(imgs, 2, 768) == one_img(480, 640, 768) + one_img(90, 120, 768) > 3 * 480 * 768
+    imgs[1].W = 0
+    assert fn(imgs, 2, 768) == -1
+    assert lib.owl_preprocess_batch(imgs, 2, one, one, 768, one, ctypes.c_longlong(1 << 30), None) != 0
+
+
 def test_layout_groups_trainables_and_qkv():
     for cfg in (synth.B32, synth.TINY, synth.L14):
         L = ParamLayout(cfg)
