@@ -194,3 +194,29 @@ def test_shadow_version_tracks_parameters_after_module_to():
     with torch.no_grad():
         p0.mul_(0.5)
     assert alias_version(model2.flat_params, [p0]) != v0
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, smoke() and bench.py's baseline legs may import it.  Static check of
+    every product module (the package except its smoke test, and the reference-facing mirrors under src/), plus a
+    dynamic one: importing the whole product leaves no `oracle` module loaded."""
+    import ast
+    offenders = []
+    for base in ("owl_vit_object_detection_b200", "src"):
+        for fn in sorted(os.listdir(os.path.join(ROOT, base))):
+            if not fn.endswith(".py") or (base, fn) == ("owl_vit_object_detection_b200", "smoke.py"):
+                continue
+            tree = ast.parse(open(os.path.join(ROOT, base, fn)).read())
+            for node in ast.walk(tree):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    mods = [node.module or ""]
+                offenders += [f"{base}/{fn}: {m}" for m in mods if m.split(".")[0] == "oracle"]
+    assert not offenders, offenders
+    code = ("import sys; sys.path.insert(0, %r); import src.models, src.losses, src.matcher, src.train_util, src.util; "
+            "import owl_vit_object_detection_b200.train, owl_vit_object_detection_b200.text, "
+            "owl_vit_object_detection_b200.preprocess, owl_vit_object_detection_b200.collective; "
+            "bad = [m for m in sys.modules if m.split('.')[0] == 'oracle']; assert not bad, bad" % ROOT)
+    subprocess.check_call([sys.executable, "-c", code])
